@@ -1,0 +1,111 @@
+/*
+ * pfb_sos.h -- C ABI of libpfb_sos.so: B200 (sm_100a) kernels for pyfilterbank's cascaded
+ * second-order-section (biquad) IIR filtering hot path.
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types cross this boundary.
+ *
+ * Layouts (identical to the reference, pyfilterbank/sosfilt.c + sosfiltering.py):
+ *   sos     : rows of 6 doubles [b0 b1 b2 a0 a1 a2] per section; a0 is read and ignored
+ *             (sosfilt.c:13,39,67).  A bank is [B][K][6] (shared by all channels) or
+ *             [C][B][K][6] (per channel, the order sosfilter_double_mimo consumes, sosfilt.c:63-68).
+ *   states  : [C][B][K][2] = (w1, w2) Direct-Form-II delay values per section (sosfilt.c:61-62,79-80).
+ *   signals : input x [C][ldx] (channel rows, time contiguous); output y [C][B][ldy]
+ *             (== the reference's (N, B, C) Fortran-ordered result, sosfiltering.py:248).
+ *
+ * Every function that can fail returns 0 on success or a negative pfb_status; the text of the
+ * last failure on the calling thread is available from pfb_last_error().  The three reference
+ * drop-ins return void like the originals: on failure they print the error to stderr, leave the
+ * buffers untouched and record the status for pfb_last_status().
+ */
+#ifndef PFB_SOS_H
+#define PFB_SOS_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PFB_API __attribute__((visibility("default")))
+#else
+#define PFB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pfb_status {
+    PFB_OK = 0,
+    PFB_ERR_INVALID = -1,   /* bad argument */
+    PFB_ERR_CUDA = -2,      /* CUDA runtime error, see pfb_last_error() */
+    PFB_ERR_NO_DEVICE = -3, /* no CUDA device: there is no CPU fallback */
+    PFB_ERR_ALLOC = -4
+} pfb_status;
+
+/* element types of signal buffers */
+#define PFB_F32 0
+#define PFB_F64 1
+
+/* flags for pfb_bank_filter() */
+#define PFB_MODE_AUTO 0x0   /* pick below from (cascades, samples) */
+#define PFB_MODE_SEQ 0x1    /* one thread per (channel, band) cascade, sequential in time */
+#define PFB_MODE_SCAN 0x2   /* time-chunked: zero-state pre-pass, state-transition carry scan, output pass */
+#define PFB_MODE_MASK 0xF
+#define PFB_EXACT 0x10      /* no FMA contraction, the reference's operation order: with PFB_MODE_SEQ the
+                               result is bit-identical to sosfilt.c */
+#define PFB_ARITH_F64 0x20  /* float32 signals, float64 coefficients/states/arithmetic */
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Reference drop-ins: the three symbols pyfilterbank/build.py:5-7 declares and
+ *    sosfiltering.py:92,149,228 call through cffi.  HOST pointers, in place, same argument meaning.
+ *    Arithmetic: sequential per cascade, separately rounded mul/add in the reference's order
+ *    (PFB_MODE_SEQ | PFB_EXACT), so results are bit-identical to the CPU reference.
+ * ---------------------------------------------------------------------------------------------- */
+PFB_API void sosfilter(float *signal, int nsamp, float *sos, int ksos, float *states);                 /* sosfilt.c:5  */
+PFB_API void sosfilter_double(double *signal, int nsamp, double *sos, int ksos, double *states);       /* sosfilt.c:31 */
+PFB_API void sosfilter_double_mimo(double *signal, int nframes, int nchan, double *sos, int ksos,      /* sosfilt.c:57 */
+                           int kbands, double *states);
+
+PFB_API int pfb_last_status(void);
+PFB_API const char *pfb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Bank objects: device-resident coefficient tables for one filter bank (what
+ *    FractionalOctaveFilterbank.sosmat holds, octbank.py:374-386).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pfb_bank pfb_bank;
+
+/* sos: HOST [rows][K][6] doubles, rows == B (shared) or C*B (per_channel != 0).
+ * The bank is created on the current CUDA device. */
+PFB_API int pfb_bank_create(pfb_bank **bank, const double *sos, int C_sos, int B, int K, int per_channel);
+PFB_API void pfb_bank_destroy(pfb_bank *bank);
+
+/* Filter C channels through the bank.  DEVICE pointers; asynchronous on `stream` (a cudaStream_t).
+ *   dtype   : PFB_F32 or PFB_F64, element type of x, y and states (states are float64 when
+ *             PFB_ARITH_F64 is set for float32 signals)
+ *   x       : [C][ldx], y : [C][B][ldy]; x may alias y only when B == 1 and ldx == ldy (in place)
+ *   states  : [C][B][K][2], read for the initial state and overwritten with the final one
+ *   n       : samples per channel (64-bit) */
+PFB_API int pfb_bank_filter(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
+                    void *states, int64_t n, int C, int flags, void *stream);
+
+/* Same on HOST buffers (pageable or pinned): streams the signal through the device in time blocks
+ * with carried states, overlapping H2D, kernels and D2H.  Synchronous. */
+PFB_API int pfb_bank_filter_host(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
+                         void *states, int64_t n, int C, int flags);
+
+/* Introspection used by the bench harness: what the last pfb_bank_filter on this bank launched. */
+typedef struct pfb_launch_info {
+    int mode;             /* PFB_MODE_SEQ or PFB_MODE_SCAN */
+    int kernels;          /* kernel launches issued */
+    int warps_per_cascade;
+    int64_t chunk;        /* samples per time chunk (scan mode), n in seq mode */
+    int64_t warm_total;   /* sum over cascades of pre-pass samples per chunk (scan mode) */
+    int aligned;          /* 16-byte vector path taken */
+} pfb_launch_info;
+PFB_API int pfb_bank_last_launch(const pfb_bank *bank, pfb_launch_info *info);
+
+PFB_API const char *pfb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFB_SOS_H */

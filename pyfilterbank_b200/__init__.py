@@ -1,0 +1,5 @@
+"""pyfilterbank_b200 -- B200-native (sm_100a) implementation of pyfilterbank's cascaded
+second-order-section IIR filtering hot path, behind the reference's Python API."""
+from .sosfiltering import (sosfilter_c, sosfilter_double_c, sosfilter_double_mimo_c,  # noqa: F401
+                           bank_filter, bilinear_sos, get_bank)
+from ._lib import Bank, PfbError  # noqa: F401

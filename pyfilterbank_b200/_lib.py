@@ -1,0 +1,113 @@
+"""ctypes binding of libpfb_sos.so (include/pfb_sos.h).  There is no CPU fallback: if the
+CUDA library is missing or no device is present, calls raise."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfb_sos.so")
+
+PFB_F32, PFB_F64 = 0, 1
+MODE_AUTO, MODE_SEQ, MODE_SCAN = 0, 1, 2
+EXACT, ARITH_F64 = 0x10, 0x20
+_MODES = {"auto": MODE_AUTO, "seq": MODE_SEQ, "scan": MODE_SCAN}
+
+
+class PfbError(RuntimeError):
+    pass
+
+
+class LaunchInfo(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int), ("kernels", ctypes.c_int), ("warps_per_cascade", ctypes.c_int),
+                ("chunk", ctypes.c_int64), ("warm_total", ctypes.c_int64), ("aligned", ctypes.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s not found: build it with `python -m pyfilterbank_b200._build` "
+                "(pyfilterbank_b200 has no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.pfb_bank_create.argtypes = [ctypes.POINTER(vp), vp, ci, ci, ci, ci]
+        L.pfb_bank_create.restype = ci
+        L.pfb_bank_destroy.argtypes = [vp]
+        L.pfb_bank_destroy.restype = None
+        L.pfb_bank_filter.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci, vp]
+        L.pfb_bank_filter.restype = ci
+        L.pfb_bank_filter_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci]
+        L.pfb_bank_filter_host.restype = ci
+        L.pfb_bank_last_launch.argtypes = [vp, ctypes.POINTER(LaunchInfo)]
+        L.pfb_bank_last_launch.restype = ci
+        L.pfb_last_error.restype = ctypes.c_char_p
+        L.pfb_last_status.restype = ci
+        L.pfb_version.restype = ctypes.c_char_p
+        fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+        L.sosfilter.argtypes = [fp, ci, fp, ci, fp]
+        L.sosfilter_double.argtypes = [dp, ci, dp, ci, dp]
+        L.sosfilter_double_mimo.argtypes = [dp, ci, ci, dp, ci, ci, dp]
+        for f in (L.sosfilter, L.sosfilter_double, L.sosfilter_double_mimo):
+            f.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PfbError("libpfb_sos error %d: %s" % (rc, lib().pfb_last_error().decode()))
+
+
+def flags_of(mode="auto", exact=False, arith64=False):
+    f = _MODES[mode]
+    if exact:
+        f |= EXACT
+    if arith64:
+        f |= ARITH_F64
+    return f
+
+
+class Bank:
+    """Device-resident coefficient tables of one filter bank (pfb_bank_create).
+
+    sos: (B, K, 6) shared by all channels, or (C, B, K, 6) per channel; rows are
+    [b0 b1 b2 a0 a1 a2] and a0 is ignored like in sosfilt.c:39."""
+
+    def __init__(self, sos):
+        sos = np.ascontiguousarray(sos, dtype=np.float64)
+        if sos.ndim == 3:
+            self.C_sos, per_channel = 1, 0
+            self.B, self.K = sos.shape[0], sos.shape[1]
+        elif sos.ndim == 4:
+            self.C_sos, per_channel = sos.shape[0], 1
+            self.B, self.K = sos.shape[1], sos.shape[2]
+        else:
+            raise ValueError("sos must be (B, K, 6) or (C, B, K, 6)")
+        if sos.shape[-1] != 6:
+            raise ValueError("sos rows must hold 6 coefficients")
+        self.per_channel = per_channel
+        h = ctypes.c_void_p()
+        check(lib().pfb_bank_create(ctypes.byref(h), sos.ctypes.data, self.C_sos, self.B, self.K, per_channel))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.pfb_bank_destroy(h)
+
+    def filter_ptr(self, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags=0, stream=0):
+        check(lib().pfb_bank_filter(self._h, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags, stream))
+
+    def filter_host(self, dtype, x, ldx, y, ldy, states, n, C, flags=0):
+        check(lib().pfb_bank_filter_host(self._h, dtype, x.ctypes.data, ldx, y.ctypes.data, ldy,
+                                         states.ctypes.data, n, C, flags))
+
+    def last_launch(self):
+        info = LaunchInfo()
+        check(lib().pfb_bank_last_launch(self._h, ctypes.byref(info)))
+        return {k: getattr(info, k) for k, _ in LaunchInfo._fields_}

@@ -1,0 +1,189 @@
+"""Second-order-section filtering on the GPU with the reference's Python signatures.
+
+Mirrors pyfilterbank/sosfiltering.py:54-248 (`sosfilter_c`, `sosfilter_double_c`,
+`sosfilter_double_mimo_c`): same argument meaning, same sos layout `[b0 b1 b2 a0 a1 a2]` per
+section, same `(w1, w2)` state layout, same return shapes and orders.  numpy in -> numpy out
+(fresh arrays, the input is never mutated); CUDA `torch.Tensor` in -> CUDA tensors out without
+leaving the device.  Extra keyword arguments (`mode`, `exact`, `arith64`) select the kernel;
+the defaults match the reference within 1e-9 relative L2 in float64.
+
+PyTorch is used for device memory and streams only; the arithmetic runs in libpfb_sos.so.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Bank
+
+__all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "bank_filter", "bilinear_sos",
+           "get_bank"]
+
+_bank_cache = collections.OrderedDict()
+
+
+def get_bank(sos):
+    """Bank for sos (B, K, 6) or (C, B, K, 6), cached by content (chunk-transition tables live
+    in the bank, so block-wise callers should not rebuild it every block)."""
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    key = (sos.shape, sos.tobytes())
+    bank = _bank_cache.get(key)
+    if bank is None:
+        bank = Bank(sos)
+        _bank_cache[key] = bank
+        if len(_bank_cache) > 32:
+            _bank_cache.popitem(last=False)
+    else:
+        _bank_cache.move_to_end(key)
+    return bank
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.PfbError("no CUDA device: pyfilterbank_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False, out=None):
+    """Filter x (C, N) CUDA tensor (float32/float64, rows contiguous) through `bank`.
+
+    Returns (y (C, B, N), states (C, B, K, 2)) CUDA tensors; `states` (if given) is updated in
+    place and returned.  This is the device-resident entry the wrappers below are built on."""
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a (C, N) CUDA tensor with contiguous rows")
+    C, N = x.shape
+    if x.dtype == torch.float64:
+        dtype, sdt = _lib.PFB_F64, torch.float64
+    elif x.dtype == torch.float32:
+        dtype, sdt = _lib.PFB_F32, (torch.float64 if arith64 else torch.float32)
+    else:
+        raise ValueError("x must be float32 or float64")
+    B, K = bank.B, bank.K
+    if states is None:
+        states = torch.zeros((C, B, K, 2), dtype=sdt, device=x.device)
+    elif states.dtype != sdt or not states.is_contiguous() or states.numel() != C * B * K * 2:
+        raise ValueError("states must be a contiguous %s tensor with C*B*K*2 elements" % sdt)
+    if out is None:
+        out = torch.empty((C, B, N), dtype=x.dtype, device=x.device)
+    ldx = x.stride(0) if C > 1 else max(N, 1)
+    with torch.cuda.device(x.device):
+        bank.filter_ptr(dtype, x.data_ptr(), ldx, out.data_ptr(), out.stride(1) if N > 0 else 1,
+                        states.data_ptr(), N, C, _lib.flags_of(mode, exact, arith64),
+                        torch.cuda.current_stream().cuda_stream)
+    return out, states
+
+
+def _sos_rows(sos):
+    sos = np.asarray(sos)
+    return np.array(sos, dtype=np.float64).reshape(-1, 6)
+
+
+def _single(signal, sos, states, np_dtype, t_dtype, mode, exact, arith64):
+    on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+    dev = signal.device if on_device else _device()
+    if isinstance(sos, torch.Tensor):
+        sos = sos.detach().cpu().numpy()
+    rows = _sos_rows(sos if np_dtype == np.float64 else np.asarray(sos, dtype=np.float32))
+    K = rows.shape[0]
+    bank = get_bank(rows.reshape(1, K, 6))
+    nsamp = len(signal)                                   # sosfiltering.py:83,140
+    if on_device:
+        x = signal.detach().to(t_dtype).reshape(-1)[:nsamp].reshape(1, nsamp)
+    else:
+        x = torch.from_numpy(np.array(signal, dtype=np_dtype).flatten()[:nsamp].reshape(1, nsamp)).to(dev)
+    sdt = torch.float64 if (np_dtype == np.float64 or arith64) else torch.float32
+    if states is None:
+        st = torch.zeros(2 * K, dtype=sdt, device=dev)
+    elif isinstance(states, torch.Tensor):
+        st = states.detach().to(device=dev, dtype=sdt).reshape(-1).clone()
+    else:
+        st = torch.from_numpy(np.array(states, dtype=np_dtype).flatten()).to(device=dev, dtype=sdt)
+    y, st = bank_filter(bank, x.contiguous(), st.reshape(1, 1, K, 2), mode=mode, exact=exact, arith64=arith64)
+    y, st = y.reshape(nsamp), st.reshape(2 * K).to(t_dtype)
+    if on_device:
+        return y, st
+    return y.cpu().numpy(), st.cpu().numpy()
+
+
+def sosfilter_c(signal, sos, states=None, *, mode="auto", exact=False, arith64=False):
+    """float32 cascade, the reference's `sosfilter_c` (sosfiltering.py:54-108): signal, sos and
+    states are cast to float32.  `exact=True` (sequential, separately rounded operations) is
+    bit-identical to sosfilt.c:5-28."""
+    return _single(signal, sos, states, np.float32, torch.float32, mode, exact, arith64)
+
+
+def sosfilter_double_c(signal, sos, states=None, *, mode="auto", exact=False):
+    """float64 cascade, the reference's `sosfilter_double_c` (sosfiltering.py:111-163)."""
+    return _single(signal, sos, states, np.float64, torch.float64, mode, exact, False)
+
+
+def sosfilter_double_mimo_c(signal, sos, states=None, *, mode="auto", exact=False):
+    """Multi-channel, multi-band float64 filtering, the reference's `sosfilter_double_mimo_c`
+    (sosfiltering.py:166-248).
+
+    signal (N,) or (N, C); sos (6K,), (6K, B) or (6K, B, C); states None, flat (C*B*K*2,) or
+    (2K, B, C).  Returns (out (N, B, C) Fortran-ordered, states flat (C*B*K*2,)), like the
+    reference.  With a CUDA tensor input the outputs are CUDA tensors: `out` is a (N, B, C) view
+    of a (C, B, N) buffer (the same memory order as the reference's Fortran array)."""
+    on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+    dev = signal.device if on_device else _device()
+    shape = tuple(signal.shape)
+    nframes = int(shape[0])
+    nchan = int(shape[1]) if len(shape) > 1 else 1
+    if isinstance(sos, torch.Tensor):
+        sos = sos.detach().cpu().numpy()
+    sos = np.asarray(sos, dtype=np.float64)
+    ksos = sos.shape[0] // 6
+    if sos.ndim == 1:
+        kbands = 1
+        bank_sos = sos.reshape(1, ksos, 6)
+    elif sos.ndim == 2:
+        kbands = sos.shape[1]
+        bank_sos = np.ascontiguousarray(sos.T).reshape(kbands, ksos, 6)          # column b = band b
+    else:
+        kbands = sos.shape[1]
+        if sos.shape[2] != nchan:
+            raise ValueError("sos has %d channels, signal has %d" % (sos.shape[2], nchan))
+        bank_sos = np.ascontiguousarray(sos.transpose(2, 1, 0)).reshape(nchan, kbands, ksos, 6)
+    bank = get_bank(bank_sos)
+    if on_device:
+        x = signal.detach().to(torch.float64).reshape(nframes, nchan).t().contiguous()
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(
+            np.array(signal, dtype=np.float64).reshape(nframes, nchan).T)).to(dev)
+    nst = nchan * kbands * ksos * 2
+    if states is None:
+        st = torch.zeros(nst, dtype=torch.float64, device=dev)
+    elif isinstance(states, torch.Tensor):
+        st = states.detach().to(device=dev, dtype=torch.float64)
+        st = (st.permute(*reversed(range(st.dim()))).contiguous() if st.dim() > 1 else st.clone()).reshape(-1)
+    else:
+        st = torch.from_numpy(np.array(states, dtype=np.float64).flatten('F')).to(dev)   # sosfiltering.py:214
+    if st.numel() != nst:
+        raise ValueError("states must hold C*B*K*2 = %d values" % nst)
+    y, st = bank_filter(bank, x, st.reshape(nchan, kbands, ksos, 2), mode=mode, exact=exact)
+    st = st.reshape(-1)
+    if on_device:
+        return y.permute(2, 1, 0), st
+    return y.cpu().numpy().transpose(2, 1, 0), st.cpu().numpy()
+
+
+def bilinear_sos(d, c):
+    """Bilinear transform of analog 1-pole-pair section weights to digital biquads
+    (the reference's `bilinear_sos`, sosfiltering.py:382-432): for each section with numerator
+    weights (d0, d1) and denominator weights (c0, c1) returns rows b, a (L/2 x 3) with a[:, 0] == 1."""
+    d = np.asarray(d)
+    c = np.asarray(c)
+    if d.ndim != 2 or c.ndim != 2 or d.shape[1] != 2 or c.shape != d.shape:
+        raise Exception('Inputs d and c must both be L/2 x 2 arrays.')
+
+    def quad(w):
+        s, t = w[:, 0] + w[:, 1], w[:, 1] - w[:, 0]
+        return np.stack([np.abs(s) ** 2, 2 * np.real(s * np.conj(t)), np.abs(t) ** 2], axis=1).astype(np.double)
+
+    a, b = quad(c), quad(d)
+    if np.min(a[:, 0]) == 0:
+        raise Exception('"c" should not have a row of zeros.')
+    norm = a[:, :1].copy()
+    return b / norm, a / norm

@@ -1,0 +1,215 @@
+"""GPU parity tests of the SOS cascade kernels against the CPU oracle (oracle/sos_oracle.c,
+itself pinned to the reference's sosfilt.c) and the golden vectors.  All calls go through the
+C ABI (libpfb_sos.so) via pyfilterbank_b200.
+
+Tolerances (BASELINE.json north_star): float64 relative L2 <= 1e-9 for the fast (FMA /
+time-chunked) paths; bit-exact for the `exact=True` sequential path in float64 AND float32.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+
+
+def _rand_sos(rng, K):
+    r = rng.uniform(0.3, 0.999, K)
+    th = rng.uniform(0.01, 3.0, K)
+    sos = np.zeros((K, 6))
+    sos[:, 0:3] = rng.standard_normal((K, 3))
+    sos[:, 3] = 1.0
+    sos[:, 4] = -2 * r * np.cos(th)
+    sos[:, 5] = r * r
+    return sos
+
+
+def _bank48():
+    g = golden("designs")
+    s = g["third_48k_o4_sosmat"]
+    return np.ascontiguousarray(s.T).reshape(s.shape[1], s.shape[0] // 6, 6)
+
+
+@pytest.fixture(scope="module")
+def pfb():
+    import pyfilterbank_b200 as p
+    assert torch.cuda.is_available()
+    return p
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8, 12])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 1000, 4099])
+def test_seq_exact_f64_bitwise(pfb, oracle, K, n):
+    rng = np.random.default_rng(100 * K + n)
+    sos = _rand_sos(rng, K)
+    x = rng.standard_normal(n)
+    st = rng.standard_normal(2 * K)
+    y0, s0 = oracle.sosfilter_double_c(x, sos, st)
+    y1, s1 = pfb.sosfilter_double_c(x, sos, st, mode="seq", exact=True)
+    assert y1.shape == (n,) and y1.dtype == np.float64
+    assert np.array_equal(y0, y1)
+    assert np.array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("K", [1, 2, 4, 6, 9])
+@pytest.mark.parametrize("n", [0, 3, 31, 32, 33, 2000, 4100])
+def test_seq_exact_f32_bitwise(pfb, oracle, K, n):
+    rng = np.random.default_rng(7 * K + n)
+    sos = _rand_sos(rng, K)
+    x = rng.standard_normal(n)
+    st = rng.standard_normal(2 * K)
+    y0, s0 = oracle.sosfilter_c(x, sos, st)
+    y1, s1 = pfb.sosfilter_c(x, sos, st, mode="seq", exact=True)
+    assert y1.dtype == np.float32
+    assert np.array_equal(y0, y1)
+    assert np.array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("mode", ["seq", "scan"])
+@pytest.mark.parametrize("n,C", [(1, 1), (100, 3), (4096, 2), (5000, 1), (5001, 2), (70001, 2)])
+def test_bank_f64_vs_oracle(pfb, oracle, mode, n, C):
+    """1/3-octave bank @48 kHz (33 bands x 4 sections), FMA arithmetic, both kernels, aligned and
+    unaligned row strides, non-zero initial states; per-band relative L2."""
+    rng = np.random.default_rng(n + C)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    x = rng.standard_normal((C, n))
+    st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+    y0, s0 = oracle.sos_bank(x, sos, st0)
+    bank = pfb.get_bank(sos)
+    xt = torch.from_numpy(x).cuda()
+    stt = torch.from_numpy(st0.copy()).cuda()
+    y1, s1 = pfb.bank_filter(bank, xt, stt, mode=mode)
+    y1, s1 = y1.cpu().numpy(), s1.cpu().numpy()
+    info = bank.last_launch()
+    assert info["mode"] == (1 if mode == "seq" else 2)
+    for b in range(B):
+        assert rel_l2(y1[:, b], y0[:, b]) <= TOL64, (b, rel_l2(y1[:, b], y0[:, b]))
+    assert rel_l2(s1, s0) <= 1e-8
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_scan_warps_and_block_carry(pfb, oracle, warps, monkeypatch):
+    """Time-chunked kernel with 32*warps chunks per cascade; two blocks with carried states equal
+    one shot (reference: block-wise == one-shot, sosfiltering.py:143-147)."""
+    monkeypatch.setenv("PFB_SCAN_WARPS", str(warps))
+    rng = np.random.default_rng(warps)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    n = 40000 + warps
+    x = rng.standard_normal((2, n))
+    y0, s0 = oracle.sos_bank(x, sos)
+    bank = pfb.get_bank(sos)
+    xt = torch.from_numpy(x).cuda()
+    cut = 12345
+    ya, st = pfb.bank_filter(bank, xt[:, :cut].contiguous(), mode="scan")
+    assert bank.last_launch()["warps_per_cascade"] == warps
+    yb, st = pfb.bank_filter(bank, xt[:, cut:].contiguous(), st, mode="scan")
+    y1 = torch.cat([ya, yb], dim=2).cpu().numpy()
+    for b in range(B):
+        assert rel_l2(y1[:, b], y0[:, b]) <= TOL64, b
+    assert rel_l2(st.cpu().numpy(), s0) <= 1e-8
+
+
+def test_mimo_golden(pfb):
+    """filter_mimo_c path: (N, C) in, (N, B, C) Fortran-ordered out, flat states, carried states."""
+    g = golden("octbank_default")
+    y, s = pfb.sosfilter_double_mimo_c(g["x"], g["sosmat"])
+    assert y.shape == (1024, 33, 2) and y.flags.f_contiguous and s.shape == (33 * 2 * 8,)
+    for b in range(33):
+        assert rel_l2(y[:, b], g["y_mimo"][:, b]) <= TOL64, b
+    y2, s2 = pfb.sosfilter_double_mimo_c(g["x"], g["sosmat"], s)
+    for b in range(33):
+        assert rel_l2(y2[:, b], g["y_mimo_block2"][:, b]) <= TOL64, b
+    # exact mode reproduces the reference bit for bit, including the flat state vector
+    y, s = pfb.sosfilter_double_mimo_c(g["x"], g["sosmat"], mode="seq", exact=True)
+    assert np.array_equal(y, g["y_mimo"]) and np.array_equal(s, g["states_mimo"])
+    # states given in the documented 3-D (2K, B, C) shape (sosfiltering.py:214 flattens 'F')
+    y2, s2 = pfb.sosfilter_double_mimo_c(g["x"], g["sosmat"], s.reshape((8, 33, 2), order='F'), mode="seq", exact=True)
+    assert np.array_equal(y2, g["y_mimo_block2"]) and np.array_equal(s2, g["states_mimo_block2"])
+
+
+def test_two_sections_golden(pfb):
+    g = golden("sos_two_sections")
+    y, s = pfb.sosfilter_double_c(g["x"], g["sos"], mode="seq", exact=True)
+    assert np.array_equal(y, g["y_double"]) and np.array_equal(s, g["states_double"])
+    y, s = pfb.sosfilter_c(g["x"], g["sos"], mode="seq", exact=True)
+    assert np.array_equal(y, g["y_float"]) and np.array_equal(s, g["states_float"])
+    y, s = pfb.sosfilter_double_c(g["x"], g["sos"])
+    assert rel_l2(y, g["y_double"]) <= TOL64
+    # the reference's own assertion (tests/test_sosfiltering.py:20-32): C vs scipy to 6 places
+    assert abs(np.sum(np.abs(y)) - np.sum(np.abs(g["y_py"]))) < 1e-6
+
+
+def test_reference_sanity_cases(pfb):
+    """tests/test_sosfiltering.py:34-40 and tests/test_octbank.py:25-37: zeros -> zeros, ones != 1."""
+    g = golden("sos_two_sections")
+    oc, _ = pfb.sosfilter_c(np.zeros(100), g["sos"])
+    assert np.all(oc == np.zeros(100))
+    oc, _ = pfb.sosfilter_c(np.ones(100), g["sos"])
+    assert np.all(oc != np.ones(100))
+    sosmat = golden("octbank_default")["sosmat"]
+    y, _ = pfb.sosfilter_double_mimo_c(np.zeros((1024, 1)), sosmat)
+    assert np.sum(y) == 0
+    y, _ = pfb.sosfilter_double_mimo_c(np.ones((1024, 1)), sosmat)
+    assert np.all(y != 1)
+
+
+def test_c_abi_dropins(pfb, oracle):
+    """The three reference symbols on host pointers (build.py:5-7), bit-identical by default."""
+    import ctypes
+    from pyfilterbank_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    K, n = 4, 3000
+    sos = _rand_sos(rng, K)
+    x = rng.standard_normal(n)
+    y0, s0 = oracle.sosfilter_double_c(x, sos)
+    sig, st, sc = x.copy(), np.zeros(2 * K), sos.flatten()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.sosfilter_double(sig.ctypes.data_as(dp), n, sc.ctypes.data_as(dp), K, st.ctypes.data_as(dp))
+    assert L.pfb_last_status() == 0
+    assert np.array_equal(sig, y0) and np.array_equal(st, s0)
+    y0, s0 = oracle.sosfilter_c(x, sos)
+    sig, st, sc = x.astype(np.float32), np.zeros(2 * K, np.float32), sos.flatten().astype(np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.sosfilter(sig.ctypes.data_as(fp), n, sc.ctypes.data_as(fp), K, st.ctypes.data_as(fp))
+    assert np.array_equal(sig, y0) and np.array_equal(st, s0)
+    # mimo: [C][B][N] pre-replicated signal, sos [C][B][K][6], states [C][B][K][2]
+    C, B = 2, 3
+    sosb = np.stack([_rand_sos(rng, K) for _ in range(C * B)]).reshape(C, B, K, 6)
+    xm = rng.standard_normal((C, n))
+    y0, s0 = oracle.sos_bank(xm, sosb)
+    sig = np.ascontiguousarray(np.repeat(xm[:, None, :], B, axis=1))
+    st = np.zeros(C * B * K * 2)
+    L.sosfilter_double_mimo(sig.ctypes.data_as(dp), n, C, sosb.ctypes.data_as(dp), K, B, st.ctypes.data_as(dp))
+    assert np.array_equal(sig, y0) and np.array_equal(st, s0.ravel())
+
+
+def test_f32_bank_modes(pfb, oracle):
+    """float32 signals: (i) float32 FMA arithmetic vs the float oracle on well-conditioned bands,
+    (ii) float64 arithmetic with float32 I/O vs the double oracle on the rounded input."""
+    rng = np.random.default_rng(11)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    n, C = 20000, 2
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    yd, _ = oracle.sos_bank(x.astype(np.float64), sos)
+    yf, _ = oracle.sos_bank(x, sos.astype(np.float32), dtype=np.float32)
+    bank = pfb.get_bank(sos)
+    xt = torch.from_numpy(x).cuda()
+    for mode in ("seq", "scan"):
+        y1, _ = pfb.bank_filter(bank, xt, mode=mode, arith64=True)
+        y1 = y1.cpu().numpy()
+        for b in range(B):
+            assert rel_l2(y1[:, b], yd[:, b]) <= 1e-6, (mode, b)       # float32 output rounding only
+        y2, _ = pfb.bank_filter(bank, xt, mode=mode)
+        y2 = y2.cpu().numpy()
+        for b in range(B):
+            ref_err = rel_l2(yf[:, b], yd[:, b])                          # the reference float path's own error
+            assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (mode, b, ref_err)
+    y3, _ = pfb.bank_filter(bank, xt, mode="seq", exact=True)
+    assert np.array_equal(y3.cpu().numpy(), yf)
