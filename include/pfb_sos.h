@@ -92,6 +92,12 @@ PFB_API int pfb_bank_filter(pfb_bank *bank, int dtype, const void *x, int64_t ld
 PFB_API int pfb_bank_filter_host(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
                          void *states, int64_t n, int C, int flags);
 
+/* Time-chunked mode hands every chunk the zero-state response to the last W samples of its
+ * predecessor (plus the exactly propagated older state).  W is chosen per band from the band's impulse
+ * response so that the dropped tail stays below `tol` relative L2 (default 1e-11, two orders under the
+ * float64 parity budget; env PFB_WARM_TOL overrides).  tol = 0 forces W = chunk length (no truncation). */
+PFB_API int pfb_bank_set_warm_tol(pfb_bank *bank, double tol);
+
 /* Introspection used by the bench harness: what the last pfb_bank_filter on this bank launched. */
 typedef struct pfb_launch_info {
     int mode;             /* PFB_MODE_SEQ or PFB_MODE_SCAN */

@@ -45,6 +45,8 @@ def lib():
         L.pfb_bank_filter_host.restype = ci
         L.pfb_bank_last_launch.argtypes = [vp, ctypes.POINTER(LaunchInfo)]
         L.pfb_bank_last_launch.restype = ci
+        L.pfb_bank_set_warm_tol.argtypes = [vp, ctypes.c_double]
+        L.pfb_bank_set_warm_tol.restype = ci
         L.pfb_last_error.restype = ctypes.c_char_p
         L.pfb_last_status.restype = ci
         L.pfb_version.restype = ctypes.c_char_p
@@ -106,6 +108,10 @@ class Bank:
     def filter_host(self, dtype, x, ldx, y, ldy, states, n, C, flags=0):
         check(lib().pfb_bank_filter_host(self._h, dtype, x.ctypes.data, ldx, y.ctypes.data, ldy,
                                          states.ctypes.data, n, C, flags))
+
+    def set_warm_tol(self, tol):
+        """Relative-L2 budget of the truncated pre-pass of the time-chunked kernel (0: exact)."""
+        check(lib().pfb_bank_set_warm_tol(self._h, float(tol)))
 
     def last_launch(self):
         info = LaunchInfo()

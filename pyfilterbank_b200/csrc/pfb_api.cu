@@ -65,11 +65,13 @@ struct pfb_bank {
     int rows = 0, B = 0, K = 0, per_channel = 0, C_sos = 0;
     std::vector<double> sos;  // [rows][K][6]
     void *coef[2] = {nullptr, nullptr};   // [PFB_F32 / PFB_F64] device [rows][K][5]
+    std::vector<double> coef_host;        // [rows][K][5] = b0 b1 b2 a1 a2
     std::vector<Sweep> sweeps;
     std::map<std::tuple<int, long long>, Tables> tables;
     std::mutex mu;
     pfb_launch_info last{};
     int sm_count = 148;
+    double warm_tol = 1e-11;   // relative L2 budget of the truncated pre-pass (0: always exact)
 };
 
 namespace {
@@ -116,18 +118,60 @@ void chunk_transition(const double *sos_row, int k0, int Ks, long long L, long d
     }
 }
 
+// Pre-pass length of sections [k0, k0+Ks) for chunk length L.  A chunk hands its successor the
+// zero-state response to its last W samples only; what is dropped is the response to the first
+// L - W samples, i.e. the tail of the cascade's impulse response h beyond lag W.  For white input the
+// error energy it leaves in the next chunk is  sum_{d=W+1..L} Tail(d),  Tail(d) = sum_{k>=d} h[k]^2,
+// against a signal energy of  L * sum h^2.  Returns the smallest W (multiple of 32) whose relative
+// L2 error estimate is <= tol, or L (exact pre-pass) if none is clearly shorter.
+long long warm_length(const double *sos_row, int k0, int Ks, long long L, double tol) {
+    if (tol <= 0 || L <= 64) return L;
+    std::vector<double> tail((size_t)L + 2, 0.0);
+    double w[16][2] = {};
+    double total = 0, recent = 0;
+    long long used = L + 1;
+    for (long long n = 0; n <= L; ++n) {
+        double x = n == 0 ? 1.0 : 0.0;
+        for (int k = 0; k < Ks; ++k) {
+            const double *q = sos_row + 6 * (k0 + k);
+            const double w0 = x - q[4] * w[k][0] - q[5] * w[k][1];
+            x = q[0] * w0 + q[1] * w[k][0] + q[2] * w[k][1];
+            w[k][1] = w[k][0];
+            w[k][0] = w0;
+        }
+        const double e = x * x;
+        tail[n] = e;
+        total += e;
+        recent += e;
+        if ((n & 1023) == 1023) {   // the response has died out: nothing later can matter
+            if (recent <= 1e-60 * total) {
+                used = n + 1;
+                break;
+            }
+            recent = 0;
+        }
+    }
+    if (!(total > 0) || !std::isfinite(total)) return L;
+    // tail[d] := sum_{k >= d} h[k]^2 (within the simulated window; beyond it the response is < 1e-30 relative)
+    for (long long d = used - 2; d >= 0; --d) tail[d] += tail[d + 1];
+    // err2(W) = sum_{d=W+1..L} tail[d]; walk W downwards from L accumulating
+    const double budget = tol * tol * (double)L * total;
+    double acc = 0;
+    long long W = L;
+    for (long long d = std::min(L, used - 1); d >= 1; --d) {
+        acc += tail[d];
+        if (acc > budget) break;
+        W = d - 1;
+    }
+    W = (W + 31) / 32 * 32;
+    if (W < 32) W = 32;
+    return W >= L - L / 8 ? L : W;
+}
+
 int ensure_coef(pfb_bank *b, int arith) {
     if (b->coef[arith]) return PFB_OK;
     const size_t n = (size_t)b->rows * b->K * 5;
-    std::vector<double> c(n);
-    for (size_t r = 0; r < (size_t)b->rows * b->K; ++r) {
-        const double *q = &b->sos[r * 6];
-        c[r * 5 + 0] = q[0];
-        c[r * 5 + 1] = q[1];
-        c[r * 5 + 2] = q[2];
-        c[r * 5 + 3] = q[4];   // a0 = q[3] is ignored like the reference does (sosfilt.c:39)
-        c[r * 5 + 4] = q[5];
-    }
+    const std::vector<double> &c = b->coef_host;
     void *d = nullptr;
     if (arith == PFB_F64) {
         PFB_CUDA(cudaMalloc(&d, n * sizeof(double)));
@@ -157,15 +201,37 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
         b->tables.clear();
     }
     Tables t;
+    const double tol = arith == PFB_F64 ? b->warm_tol : (b->warm_tol > 0 ? std::max(b->warm_tol, 1e-8) : 0.0);
+    // rows with identical coefficients (a bank tiled per channel) share their tables
+    std::map<std::string, int> first_row;
+    std::vector<int> same_as(b->rows);
+    for (int r = 0; r < b->rows; ++r) {
+        std::string key((const char *)&b->sos[(size_t)r * b->K * 6], (size_t)b->K * 6 * sizeof(double));
+        same_as[r] = first_row.emplace(std::move(key), r).first->second;
+    }
     for (const Sweep &sw : b->sweeps) {
         const int S = 2 * sw.K;
         const size_t per = (size_t)S * S, n = per * b->rows;
         std::vector<long double> R(per);
         std::vector<double> Pd(n);
+        std::vector<int> warm(b->rows);
         for (int r = 0; r < b->rows; ++r) {
-            chunk_transition(&b->sos[(size_t)r * b->K * 6], sw.k0, sw.K, L, R.data());
-            for (size_t i = 0; i < per; ++i) Pd[r * per + i] = (double)R[i];
+            const int o = same_as[r];
+            if (o != r) {
+                std::copy(&Pd[o * per], &Pd[o * per] + per, &Pd[r * per]);
+                warm[r] = warm[o];
+            } else {
+                const double *row = &b->sos[(size_t)r * b->K * 6];
+                chunk_transition(row, sw.k0, sw.K, L, R.data());
+                for (size_t i = 0; i < per; ++i) Pd[r * per + i] = (double)R[i];
+                warm[r] = (int)std::min<long long>(warm_length(row, sw.k0, sw.K, L, tol), 0x7fffffff);
+            }
+            t.warm_total += std::min<long long>(warm[r], L);
         }
+        int *dw = nullptr;
+        PFB_CUDA(cudaMalloc(&dw, b->rows * sizeof(int)));
+        PFB_CUDA(cudaMemcpy(dw, warm.data(), b->rows * sizeof(int), cudaMemcpyHostToDevice));
+        t.warm.push_back(dw);
         void *d = nullptr;
         if (arith == PFB_F64) {
             PFB_CUDA(cudaMalloc(&d, n * sizeof(double)));
@@ -176,8 +242,6 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
             PFB_CUDA(cudaMemcpy(d, Pf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         }
         t.P.push_back(d);
-        t.warm.push_back(nullptr);
-        t.warm_total += (long long)b->rows * L;
     }
     auto ins = b->tables.emplace(key, std::move(t));
     *out = &ins.first->second;
@@ -227,7 +291,15 @@ int pfb_bank_create(pfb_bank **out, const double *sos, int C_sos, int B, int K, 
     b->rows = b->C_sos * B;
     b->sos.assign(sos, sos + (size_t)b->rows * K * 6);
     b->sweeps = split_sweeps(K);
+    b->coef_host.resize((size_t)b->rows * K * 5);
+    for (size_t r = 0; r < (size_t)b->rows * K; ++r) {
+        const double *q = &b->sos[r * 6];
+        double *c = &b->coef_host[r * 5];
+        c[0] = q[0], c[1] = q[1], c[2] = q[2];
+        c[3] = q[4], c[4] = q[5];   // a0 = q[3] is ignored like the reference does (sosfilt.c:39)
+    }
     cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (const char *v = getenv("PFB_WARM_TOL")) b->warm_tol = atof(v);
     *out = b;
     g_status = PFB_OK;
     return PFB_OK;
@@ -242,6 +314,21 @@ void pfb_bank_destroy(pfb_bank *b) {
         for (int *p : kv.second.warm) cudaFree(p);
     }
     delete b;
+}
+
+int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
+    if (!b || !(tol >= 0)) return fail(PFB_ERR_INVALID, "pfb_bank_set_warm_tol: bad argument");
+    std::lock_guard<std::mutex> lock(b->mu);
+    if (tol != b->warm_tol) {
+        cudaDeviceSynchronize();   // nothing may still be reading the tables built for the old tolerance
+        for (auto &kv : b->tables) {
+            for (void *p : kv.second.P) cudaFree(p);
+            for (int *p : kv.second.warm) cudaFree(p);
+        }
+        b->tables.clear();
+        b->warm_tol = tol;
+    }
+    return PFB_OK;
 }
 
 int pfb_bank_last_launch(const pfb_bank *b, pfb_launch_info *info) {
@@ -293,8 +380,11 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
         const long long lanes_to_fill = (long long)b->sm_count * 16 * 32;
         mode = (exact || Qll >= lanes_to_fill / 2 || n < 4 * tlen) ? PFB_MODE_SEQ : PFB_MODE_SCAN;
     }
-    int rc = ensure_coef(b, arith);
-    if (rc) return rc;
+    int rc = PFB_OK;
+    if (mode == PFB_MODE_SEQ) {
+        rc = ensure_coef(b, arith);
+        if (rc) return rc;
+    }
 
     int warps = 1;
     long long L = n;
@@ -347,13 +437,14 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
         } else {
             p.P = tab->P[si];
             p.warm = tab->warm[si];
-            err = dtype == PFB_F64 ? pfb::launch_scan_dd(p, sw.K, warps, stream)
-                  : arith64       ? pfb::launch_scan_fd(p, sw.K, warps, stream)
-                                  : pfb::launch_scan_ff(p, sw.K, warps, stream);
+            const double *ch = b->coef_host.data();
+            err = dtype == PFB_F64 ? pfb::launch_scan_dd(p, sw.K, warps, ch, b->rows, C, stream, &launches)
+                  : arith64       ? pfb::launch_scan_fd(p, sw.K, warps, ch, b->rows, C, stream, &launches)
+                                  : pfb::launch_scan_ff(p, sw.K, warps, ch, b->rows, C, stream, &launches);
         }
         if (err != 0)
             return fail(PFB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
-        ++launches;
+        if (mode == PFB_MODE_SEQ) ++launches;
     }
     b->last.mode = mode;
     b->last.kernels = launches;
