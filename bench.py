@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- channel*band samples/s of the 1/3-octave MIMO filter bank on N B200 GPUs.
+
+Workload (BASELINE.json configs[1]): 1/3-octave Butterworth bank at 48 kHz (33 bands x 4 biquads,
+the FractionalOctaveFilterbank defaults at fs=48000), 64 channels x 60 s of white noise PER GPU,
+float64 (default) or float32.  One step = one pass of the bank over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl ours|reference]
+
+`value` is timed with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max
+over ranks).  `e2e` is the same pass through the C ABI on HOST buffers (pfb_bank_filter_host:
+pinned host input, H2D, kernels, D2H of every band signal inside the timed region).
+`--impl reference` times the reference's own C (oracle/_ref, built from the unmodified sosfilt.c)
+on the host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 48000
+SECONDS = 60
+CHANNELS_PER_GPU = 64
+METRIC = "channel*band samples/s (1/3-oct MIMO bank)"
+UNIT = "band-samples/s"
+
+
+def bank_sos():
+    from pyfilterbank_b200.octbank import FractionalOctaveFilterbank
+    import pyfilterbank_b200.octbank as ob
+    # design only (numpy); constructing the class does not touch the GPU
+    cf, edges = ob.frequencies_fractional_octaves(-19, 13, 1000.0, 3.0)
+    sosmat = ob.design_sosmat_band_passes(4, edges, FS, 0.01)
+    B = sosmat.shape[1]
+    return np.ascontiguousarray(sosmat.T).reshape(B, 4, 6)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smmax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:   # region shorter than the sampling period: use the nearest samples
+            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) > 2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
+    """Reference C (`sosfilter_double`, sosfilt.c:31-54, via ctypes) over all host cores:
+    work items are (channel, band) cascades of a bounded sample of the workload."""
+    import ctypes
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as o
+    o.build()
+    kind = "reference" if o.have_ref() else "port"
+    fn = o.ref().sosfilter_double if kind == "reference" else o.lib().oracle_sosfilter_double
+    cores = cores or os.cpu_count() or 1
+    B, K = sos.shape[:2]
+    seconds = seconds or 20
+    n = FS * seconds
+    C = cores                     # one channel per core so every thread has B cascades of work
+    rng = np.random.default_rng(1234)
+    x = 0.1 * rng.standard_normal((C, n))
+    dp = ctypes.POINTER(ctypes.c_double)
+    sos_rows = [np.ascontiguousarray(sos[b]).reshape(-1) for b in range(B)]
+
+    def work(c):
+        buf = np.empty(n)
+        st = np.zeros(2 * K)
+        for b in range(B):
+            np.copyto(buf, x[c])
+            st[:] = 0
+            if kind == "reference":
+                fn(buf.ctypes.data_as(dp), n, sos_rows[b].ctypes.data_as(dp), K, st.ctypes.data_as(dp))
+            else:
+                fn(buf.ctypes.data_as(dp), n, sos_rows[b].ctypes.data_as(dp), K, st.ctypes.data_as(dp))
+        return buf[-1]
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            list(ex.map(work, range(C)))
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    per_step = float(np.mean(times))
+    value = C * B * n / per_step
+    sample = "%d channels x %d bands x %d s @ %d Hz float64 per step, %s via ctypes, %d threads" % (
+        C, B, seconds, FS, "oracle/_ref sosfilter_double (unmodified sosfilt.c, gcc -O3)"
+        if kind == "reference" else "oracle port", cores)
+    return value, per_step, {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seconds", type=int, default=SECONDS)
+    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    sos = bank_sos()
+    B, K = sos.shape[:2]
+    n = FS * args.seconds
+    C = args.channels
+    esz = 8 if args.dtype == "f64" else 4
+    config = {"workload": "1/3-octave filter_mimo_c bank, %d channels x %d s @ %d Hz per GPU, %s" % (
+                  C, args.seconds, FS, "float64" if esz == 8 else "float32"),
+              "bands": B, "sections_per_band": K, "channels_per_gpu": C, "samples": n,
+              "sharding": "channels, no collective on the filtering path",
+              "l2": "inputs (%.2f GB) and outputs (%.1f GB) exceed the 126 MB L2; no flush needed" % (
+                  C * n * esz / 1e9, C * B * n * esz / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        value, per_step, cpu = cpu_reference_run(args.steps, max(args.warmup, 1), sos)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cpu,
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pyfilterbank_b200 as pfb
+    from pyfilterbank_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdt = torch.float64 if esz == 8 else torch.float32
+    bank = pfb.Bank(sos)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x = torch.randn((C, n), generator=gen, device=dev, dtype=tdt) * 0.1
+    y = torch.empty((C, B, n), device=dev, dtype=tdt)
+    states = torch.zeros((C, B, K, 2), device=dev, dtype=tdt)
+
+    def step():
+        states.zero_()
+        pfb.bank_filter(bank, x, states, out=y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    info = bank.last_launch()
+    ms_per_step = ms / args.steps
+    total_units = world * C * B * n
+    value = total_units / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (one filtering kernel per step): algorithmic bytes = every band
+    # sample written once + every input sample read once
+    alg_bytes = C * n * esz * (B + 1)
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        # dram bytes per band-sample from the committed ncu capture, scaled to this launch
+        per_unit = tj.get(args.dtype, {}).get("dram_bytes_per_band_sample")
+        if per_unit:
+            traffic = per_unit * C * B * n
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "sos_scan_kernel" if info["mode"] == 2 else "sos_seq_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes}
+
+    # optional gather of a bounded slab of band outputs, timed separately (never inside `value`)
+    gather = None
+    if world > 1:
+        from pyfilterbank_b200.sharding import gather_bands
+        ns = FS  # one second of every band of every local channel
+        slab = y[:, :, :ns].contiguous()
+        gather_bands(slab, world * C)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = gather_bands(slab, world * C)
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1)
+        t = torch.tensor([gms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        gather = {"ms": gms, "bytes_received_per_rank": int(full.numel() * esz),
+                  "GBps_per_rank": full.numel() * esz / (gms * 1e-3) / 1e9,
+                  "what": "all_gather_into_tensor (NCCL) of 1 s of every band; reported separately"}
+        del full, slab
+
+    # end to end through the C ABI on host buffers
+    e2e = None
+    if not args.no_e2e:
+        del y
+        torch.cuda.empty_cache()
+        e2e_steps = max(1, min(2, args.steps))
+        xh = torch.empty((C, n), dtype=tdt, pin_memory=True)
+        xh.copy_(x.cpu())
+        yh = torch.empty((C, B, n), dtype=tdt, pin_memory=True)
+        sth = np.zeros((C, B, K, 2), dtype=np.float64 if esz == 8 else np.float32)
+        dtype_code = _lib.PFB_F64 if esz == 8 else _lib.PFB_F32
+
+        def e2e_step():
+            sth[:] = 0
+            _lib.check(_lib.lib().pfb_bank_filter_host(bank._h, dtype_code, xh.data_ptr(), n, yh.data_ptr(), n,
+                                                       sth.ctypes.data, n, C, 0))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_units / dt, "unit": UNIT, "h2d_bytes_per_step": int(C * n * esz + sth.nbytes),
+               "d2h_bytes_per_step": int(C * B * n * esz + sth.nbytes), "ms_per_step": dt * 1e3,
+               "steps": e2e_steps, "api": "pfb_bank_filter_host (C ABI, pinned host buffers)",
+               "checksum": float(yh[0, B // 2, :1000].double().abs().sum())}
+        del xh, yh
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        _, _, cpu = cpu_reference_run(2, 1, sos, seconds=10)
+
+    if rank == 0:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                          "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "gpu_launches": int(info["kernels"]) * args.steps, "clocks": clocks,
+                          "launch": info, "gather": gather}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

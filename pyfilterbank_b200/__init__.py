@@ -3,3 +3,5 @@ second-order-section IIR filtering hot path, behind the reference's Python API."
 from .sosfiltering import (sosfilter_c, sosfilter_double_c, sosfilter_double_mimo_c,  # noqa: F401
                            bank_filter, bilinear_sos, get_bank)
 from ._lib import Bank, PfbError  # noqa: F401
+from .octbank import FractionalOctaveFilterbank  # noqa: F401,E402
+from . import butterworth, octbank, sosfiltering, sharding  # noqa: F401,E402

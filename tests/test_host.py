@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic: coefficient design vs the reference's (golden designs),
+the C-ABI library (loads, exports every declared symbol, fails loudly without a GPU), and the
+channel-sharding helpers over a 2-rank gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+
+def test_butter_sos_matches_reference():
+    from pyfilterbank_b200 import butterworth as bw
+    g = golden("designs")
+    for band, args in {"lowpass": (4, 0.1), "highpass": (4, 0.2), "bandpass": (4, 0.1, 0.2),
+                       "bandstop": (2, 0.15, 0.3)}.items():
+        s = bw.butter_sos(band, *args)
+        assert s.shape == g["butter_" + band].shape
+        np.testing.assert_allclose(s, g["butter_" + band], rtol=1e-13, atol=1e-15)
+        assert np.all(s[:, 3] == 1.0)
+    with pytest.raises(Exception):
+        bw.butter_sos("lowpass", 3, 0.1)        # odd pole count (butterworth.py:88-89)
+    with pytest.raises(Exception):
+        bw.butter_sos("lowpass", 4, 0.6)        # v1 >= 0.5 (butterworth.py:44-45)
+    with pytest.raises(Exception):
+        bw.butter_sos("bandpass", 4, 0.2, 0.1)  # v2 <= v1
+
+
+def test_octbank_design_matches_reference():
+    from pyfilterbank_b200 import octbank as ob
+    g = golden("designs")
+    for name, kw in {"third_48k_o4": dict(sample_rate=48000, order=4, nth_oct=3.0),
+                     "twelfth_48k_o6": dict(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51),
+                     "octave_44k_o2": dict(sample_rate=44100, order=2, nth_oct=1.0, start_band=-5, end_band=4)}.items():
+        cf, edges = ob.frequencies_fractional_octaves(kw.get("start_band", -19), kw.get("end_band", 13), 1000.0,
+                                                      kw["nth_oct"])
+        assert np.array_equal(cf, g[name + "_cf"]) and np.array_equal(edges, g[name + "_edges"])
+        sosmat = ob.design_sosmat_band_passes(kw["order"], edges, kw["sample_rate"], 0.01)
+        np.testing.assert_allclose(sosmat, g[name + "_sosmat"], rtol=1e-13, atol=0)
+    d = golden("octbank_default")
+    cf, edges = ob.frequencies_fractional_octaves(-19, 13, 1000.0, 3.0)
+    sosmat = ob.design_sosmat_band_passes(4, edges, 44100, 0.01)     # top edge clipped to 0.499 fs
+    np.testing.assert_allclose(sosmat, d["sosmat"], rtol=1e-13, atol=0)
+    # the reference's own design tests (tests/test_octbank.py:49-64)
+    cf, edges = ob.frequencies_fractional_octaves(-20, 20, 1000.0, 3.0)
+    assert cf[-20 - 1] == 1000.0 and len(cf) == 41 and len(edges) == 42
+    assert np.all(np.isfinite(ob.design_sosmat_band_passes(2, edges, 44100)))
+
+
+def test_bilinear_sos_errors():
+    from pyfilterbank_b200.sosfiltering import bilinear_sos
+    with pytest.raises(Exception):
+        bilinear_sos(np.ones((2, 3)), np.ones((2, 2)))
+    with pytest.raises(Exception):
+        bilinear_sos(np.ones((2, 2)), np.zeros((2, 2)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from pyfilterbank_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "pfb_sos.h")).read()
+    names = re.findall(r"PFB_API\s+[\w\s\*]+?\b(\w+)\s*\(", header)
+    assert {"sosfilter", "sosfilter_double", "sosfilter_double_mimo", "pfb_bank_create", "pfb_bank_filter",
+            "pfb_bank_filter_host"} <= set(names)
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"sm_100a" in L.pfb_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import pyfilterbank_b200 as pfb
+    with pytest.raises(pfb.PfbError):
+        pfb.sosfilter_double_c(np.zeros(8), np.array([[1, 0, 0, 1, 0, 0.]]))
+    h = ctypes.c_void_p()
+    from pyfilterbank_b200 import _lib
+    rc = _lib.lib().pfb_bank_create(ctypes.byref(h), np.array([1, 0, 0, 1, 0, 0.]).ctypes.data, 1, 1, 1, 0)
+    assert rc == -3 and b"no CPU fallback" in _lib.lib().pfb_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pyfilterbank_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), (f, "the product path must not reference the CPU checker")
+
+
+def test_shard_channels():
+    from pyfilterbank_b200.sharding import shard_channels
+    for C in (1, 7, 64, 8192):
+        for W in (1, 2, 3, 8):
+            spans = [shard_channels(C, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == C
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from pyfilterbank_b200.sharding import shard_channels, gather_bands
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+C, B, n = 5, 3, 16                      # ragged: rank 0 gets 3 channels, rank 1 gets 2
+full = torch.arange(C * B * n, dtype=torch.float64).reshape(C, B, n)
+c0, c1 = shard_channels(C, world, rank)
+got = gather_bands(full[c0:c1].clone(), C)
+assert torch.equal(got, full), "gathered slab differs"
+got2 = gather_bands(full[c0:c1].clone())          # sizes discovered by a collective
+assert torch.equal(got2, full)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gather_bands_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
