@@ -109,6 +109,24 @@ typedef struct pfb_launch_info {
 } pfb_launch_info;
 PFB_API int pfb_bank_last_launch(const pfb_bank *bank, pfb_launch_info *info);
 
+/* ------------------------------------------------------------------------------------------------
+ * 3. The two scipy.signal.lfilter recurrences on the path.  DEVICE pointers, asynchronous on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* GammatoneFilterbank.analyze / fosfilter (gammatone.py:196-237, :313-316): `order` passes of the
+ * complex one-pole  y = z + g*x ; z = c*y  per band, gain in the first pass only.
+ *   x [C][ldx] real float64; y [C][B][ldy] complex128 interleaved (ldy in complex elements);
+ *   coef HOST [B][3] = (gain, Re c, Im c) with c = -a[1] of the reference's (b, a);
+ *   states [C][B][order][2] complex, scipy's zi convention (c * last output of the stage), in/out. */
+PFB_API int pfb_fos_bank_c128(const double *x, int64_t ldx, double *y, int64_t ldy, const double *coef, int B,
+                              int order, double *states, int64_t n, int C, void *stream);
+
+/* splweighting.weight_signal (splweighting.py:79-80): y = lfilter(b, a, x) per row, direct form II
+ * transposed in scipy's operation order; b, a HOST arrays (at most 8 taps); z [R][max(nb,na)-1] delay
+ * values in/out (zeros for the reference's behaviour). */
+PFB_API int pfb_tf_filter_f64(const double *x, int64_t ldx, double *y, int64_t ldy, const double *b, int nb,
+                              const double *a, int na, double *z, int64_t n, int R, void *stream);
+
 PFB_API const char *pfb_version(void);
 
 #ifdef __cplusplus

@@ -4,4 +4,5 @@ from .sosfiltering import (sosfilter_c, sosfilter_double_c, sosfilter_double_mim
                            bank_filter, bilinear_sos, get_bank)
 from ._lib import Bank, PfbError  # noqa: F401
 from .octbank import FractionalOctaveFilterbank  # noqa: F401,E402
-from . import butterworth, octbank, sosfiltering, sharding  # noqa: F401,E402
+from .gammatone import GammatoneFilterbank  # noqa: F401,E402
+from . import butterworth, octbank, sosfiltering, sharding, gammatone, splweighting  # noqa: F401,E402

@@ -47,6 +47,10 @@ def lib():
         L.pfb_bank_last_launch.restype = ci
         L.pfb_bank_set_warm_tol.argtypes = [vp, ctypes.c_double]
         L.pfb_bank_set_warm_tol.restype = ci
+        L.pfb_fos_bank_c128.argtypes = [vp, i64, vp, i64, vp, ci, ci, vp, i64, ci, vp]
+        L.pfb_fos_bank_c128.restype = ci
+        L.pfb_tf_filter_f64.argtypes = [vp, i64, vp, i64, vp, ci, vp, ci, vp, i64, ci, vp]
+        L.pfb_tf_filter_f64.restype = ci
         L.pfb_last_error.restype = ctypes.c_char_p
         L.pfb_last_status.restype = ci
         L.pfb_version.restype = ctypes.c_char_p

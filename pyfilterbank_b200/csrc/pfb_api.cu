@@ -267,6 +267,12 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
 
+int pfb_set_error(int status, const char *msg) {   // used by the other translation units
+    g_status = status;
+    g_error = msg ? msg : "";
+    return status;
+}
+
 extern "C" {
 
 int pfb_last_status(void) { return g_status; }

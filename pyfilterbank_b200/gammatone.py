@@ -1,0 +1,183 @@
+"""Gammatone filter bank analysis on the GPU (Hohmann 2002), with the reference's interface.
+
+Mirrors pyfilterbank/gammatone.py: the ERB-scale helpers (:44-141), `design_filter` (:144-193),
+`fosfilter` (:196-237) and `GammatoneFilterbank.analyze` (:272-316).  Every band is `order` passes
+of a complex one-pole  y[n] = g*x[n] + c*y[n-1]  (gain in the first pass only); the reference runs
+them through scipy.signal.lfilter, here all bands (and all signals of a batch) run in one launch of
+libpfb_sos.so (pfb_fos_bank_c128).  States use scipy's convention (c times the stage's last output),
+so they can be carried between blocks -- which the reference's own code cannot do (its `if not
+states:` raises on an array, gammatone.py:229).
+
+The synthesis side (`reanalyze`, `synthesize`, `delay`) is host-side bookkeeping around the same
+filter and is not part of the accelerated path.
+"""
+import numpy as np
+import torch
+from numpy import pi
+
+from . import _lib
+from .sosfiltering import _device
+
+_ERB_L = 24.7
+_ERB_Q = 9.265
+
+
+def erb_count(centerfrequency):
+    """Number of equivalent rectangular bandwidths below `centerfrequency` (Hz)."""
+    return 21.4 * np.log10(4.37 * 0.001 * centerfrequency + 1)
+
+
+def erb_aud(centerfrequency):
+    """Equivalent rectangular bandwidth of the auditory filter at `centerfrequency` (Hohmann eq. 13)."""
+    return _ERB_L + centerfrequency / _ERB_Q
+
+
+def hertz_to_erbscale(frequency):
+    """Hz -> ERB scale (Hohmann eq. 16)."""
+    return _ERB_Q * np.log(1 + frequency / (_ERB_L * _ERB_Q))
+
+
+def erbscale_to_hertz(erb):
+    """ERB scale -> Hz (Hohmann eq. 17)."""
+    return (np.exp(erb / _ERB_Q) - 1) * _ERB_L * _ERB_Q
+
+
+def frequencies_gammatone_bank(start_band, end_band, norm_freq, density):
+    """Centre frequencies `density` ERB apart, from start_band to end_band (exclusive) ERB around
+    norm_freq; gammatone.py:118-141."""
+    return erbscale_to_hertz(np.arange(start_band, end_band, density) + hertz_to_erbscale(norm_freq))
+
+
+def design_filter(sample_rate=44100, order=4, centerfrequency=1000.0, band_width=None, band_width_factor=1.0,
+                  attenuation_half_bandwidth_db=-3):
+    """(b, a) = ([gain], [1, -coef]) of one gammatone stage; gammatone.py:144-193."""
+    if band_width:
+        phi = pi * band_width / sample_rate
+    elif band_width_factor:
+        phi = pi * band_width_factor * erb_aud(centerfrequency) / sample_rate
+    else:
+        raise ValueError('You need to specify either `band_width` or `band_width_factor!`')
+    alpha = 10 ** (0.1 * attenuation_half_bandwidth_db / order)
+    p = (-2 + 2 * alpha * np.cos(phi)) / (1 - alpha)
+    lambda_ = -p / 2 - np.sqrt(p * p / 4 - 1)
+    beta = 2 * pi * centerfrequency / sample_rate
+    coef = lambda_ * np.exp(1j * beta)
+    factor = 2 * (1 - np.abs(coef)) ** order
+    return np.array([factor]), np.array([1., -coef])
+
+
+def design_filtbank_coeffs(samplerate, order, centerfrequencies, bandwidths=None, bandwidth_factor=None,
+                           attenuation_half_bandwidth_db=-3):
+    for i, cf in enumerate(centerfrequencies):
+        bw, bwf = (bandwidths[i], None) if bandwidths else (None, bandwidth_factor)
+        yield design_filter(samplerate, order, cf, band_width=bw, band_width_factor=bwf,
+                            attenuation_half_bandwidth_db=attenuation_half_bandwidth_db)
+
+
+def fos_bank(x, coef, order, states=None):
+    """Run B complex one-pole cascades over every row of x.
+
+    x (C, N) CUDA float64 tensor; coef (B, 3) numpy rows (gain, Re c, Im c); states (C, B, order)
+    complex128 CUDA tensor or None.  Returns (bands (C, B, N) complex128, states)."""
+    C, N = x.shape
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    B = coef.shape[0]
+    if states is None:
+        states = torch.zeros((C, B, order), dtype=torch.complex128, device=x.device)
+    y = torch.empty((C, B, N), dtype=torch.complex128, device=x.device)
+    if N > 0:
+        x = x.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().pfb_fos_bank_c128(x.data_ptr(), N, y.data_ptr(), N, coef.ctypes.data, B, order,
+                                                     states.data_ptr(), N, C,
+                                                     torch.cuda.current_stream().cuda_stream))
+    return y, states
+
+
+def _coef_rows(coeffs):
+    return np.array([[np.real(b[0]), np.real(-a[1]), np.imag(-a[1])] for b, a in coeffs], dtype=np.float64)
+
+
+def fosfilter(b, a, order, signal, states=None):
+    """`order` passes of the first-order section (b, a) over `signal`; returns (complex128 signal,
+    complex128 states[order]); gammatone.py:196-237.  numpy in -> numpy out, CUDA tensor in ->
+    CUDA tensors out."""
+    on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+    dev = signal.device if on_device else _device()
+    if on_device:
+        if signal.is_complex():
+            signal = signal.real
+        x = signal.to(torch.float64).reshape(1, -1)
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(np.real(signal), dtype=np.float64).reshape(1, -1)).to(dev)
+    st = None
+    if states is not None:
+        st = torch.as_tensor(np.asarray(states.cpu() if isinstance(states, torch.Tensor) else states,
+                                        dtype=np.complex128)).reshape(1, 1, order).to(dev)
+    y, st = fos_bank(x, _coef_rows([(b, a)]), order, st)
+    y, st = y.reshape(-1), st.reshape(order)
+    return (y, st) if on_device else (y.cpu().numpy(), st.cpu().numpy())
+
+
+def _create_impulse(num_samples):
+    sig = np.zeros(int(num_samples)) + 0j
+    sig[0] = 1.0
+    return sig
+
+
+class GammatoneFilterbank:
+    """Same constructor as the reference (gammatone.py:272-311).  `analyze(signal, states=None)` is a
+    generator of (band, states) tuples in ascending centre frequency; a 2-D signal (C, N) is treated
+    as a batch and yields bands of shape (C, N)."""
+
+    def __init__(self, samplerate=44100, order=4, startband=-12, endband=12, normfreq=1000.0, density=1.0,
+                 bandwidth_factor=1.0, desired_delay_sec=0.02):
+        self.samplerate = samplerate
+        self.order = order
+        self.centerfrequencies = frequencies_gammatone_bank(startband, endband, normfreq, density)
+        self._coeffs = tuple(design_filtbank_coeffs(samplerate, order, self.centerfrequencies,
+                                                    bandwidth_factor=bandwidth_factor))
+        self._coef_rows = _coef_rows(self._coeffs)
+        self.init_delay(desired_delay_sec)
+        self.init_gains()
+
+    def init_delay(self, desired_delay_sec):
+        self.desired_delay_sec = desired_delay_sec
+        self.desired_delay_samples = int(self.samplerate * desired_delay_sec)
+        self.max_indices, self.slopes = self.estimate_max_indices_and_slopes(
+            delay_samples=self.desired_delay_samples)
+        self.delay_samples = self.desired_delay_samples - self.max_indices
+        self.delay_memory = np.zeros((len(self.centerfrequencies), np.max(self.delay_samples)))
+
+    def init_gains(self):
+        self.gains = np.ones(len(self.centerfrequencies))
+
+    def analyze(self, signal, states=None):
+        on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
+        dev = signal.device if on_device else _device()
+        if on_device:
+            x = (signal.real if signal.is_complex() else signal).to(torch.float64)
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(np.real(signal), dtype=np.float64)).to(dev)
+        batched = x.dim() == 2
+        x = x.reshape(-1, x.shape[-1])
+        C, B = x.shape[0], len(self._coeffs)
+        st = None
+        if states is not None and len(states):
+            rows = [np.asarray(s.cpu() if isinstance(s, torch.Tensor) else s, dtype=np.complex128) for s in states]
+            st = torch.as_tensor(np.stack(rows).reshape(B, C, self.order)).permute(1, 0, 2).contiguous().to(dev)
+        y, st = fos_bank(x, self._coef_rows, self.order, st)
+        if not on_device:
+            y, st = y.cpu().numpy(), st.cpu().numpy()
+        for i in range(B):
+            band = y[:, i] if batched else y[0, i]
+            yield band, (st[:, i] if batched else st[0, i])
+
+    def estimate_max_indices_and_slopes(self, delay_samples=None):
+        if not delay_samples:
+            delay_samples = int(self.samplerate / 10)
+        sig = _create_impulse(delay_samples)
+        bands = list(zip(*self.analyze(sig)))[0]
+        ibandmax = [np.argmax(np.abs(b[:delay_samples])) for b in bands]
+        slopes = [b[i + 1] - b[i - 1] for (b, i) in zip(bands, ibandmax)]
+        return np.array(ibandmax), np.array(slopes)
