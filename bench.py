@@ -225,6 +225,8 @@ def main():
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # per-kernel CUDA events inside the library, recorded on the launching stream during the timed steps
+    bank.timing_begin(args.steps)
     barrier()
     w0 = time.time()
     e0.record()
@@ -234,6 +236,7 @@ def main():
     barrier()
     w1 = time.time()
     ms = e0.elapsed_time(e1)
+    kt = bank.timing_end()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -244,11 +247,17 @@ def main():
     total_units = world * C * B * n
     value = total_units / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (one filtering kernel per step): algorithmic bytes = every band
-    # sample written once + every input sample read once
+    # roofline of the dominant kernel (the output pass: reads every input sample, writes every band
+    # sample).  algorithmic bytes per launch = (B + 1) * C * n * element size (s_out + s_in / B
+    # per band-sample); duration = that kernel's mean launch time from the library's CUDA events over the
+    # timed steps.  `step_frac` is the same bytes over the WHOLE step (pre-pass + carry + output pass).
     alg_bytes = C * n * esz * (B + 1)
     peak, peak_src = peaks()
-    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    tma = info["aligned"] == 2
+    kname = ("sos_tma_kernel<PASS_B> (output pass)" if tma else
+             "sos_scan_kernel" if info["mode"] == 2 else "sos_seq_kernel")
+    kms = kt["output"] if kt["calls"] else ms_per_step
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -259,9 +268,11 @@ def main():
         if per_unit:
             traffic = per_unit * C * B * n
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "sos_scan_kernel" if info["mode"] == 2 else "sos_seq_kernel",
-                "algorithmic_bytes_per_launch": alg_bytes}
+                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "kernels_ms": {k: kt[k] for k in ("prepass", "carry", "output", "total")},
+                "kernel_share_of_step": kms / ms_per_step}
 
     # optional gather of a bounded slab of band outputs, timed separately (never inside `value`)
     gather = None

@@ -109,6 +109,14 @@ typedef struct pfb_launch_info {
 } pfb_launch_info;
 PFB_API int pfb_bank_last_launch(const pfb_bank *bank, pfb_launch_info *info);
 
+/* Per-kernel device times for the bench harness.  timing_begin arms CUDA events for the next
+ * `max_calls` pfb_bank_filter calls on this bank (recorded on the stream each call is launched on);
+ * timing_end waits for them and returns the mean milliseconds per call of
+ *   ms[0] pre-pass kernel, ms[1] carry kernel, ms[2] output kernel, ms[3] whole call
+ * (paths that launch a single kernel book everything on ms[2]) and how many calls were recorded. */
+PFB_API int pfb_bank_timing_begin(pfb_bank *bank, int max_calls);
+PFB_API int pfb_bank_timing_end(pfb_bank *bank, double *ms, int *calls);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. The two scipy.signal.lfilter recurrences on the path.  DEVICE pointers, asynchronous on `stream`.
  * ---------------------------------------------------------------------------------------------- */

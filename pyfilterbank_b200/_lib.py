@@ -45,6 +45,10 @@ def lib():
         L.pfb_bank_filter_host.restype = ci
         L.pfb_bank_last_launch.argtypes = [vp, ctypes.POINTER(LaunchInfo)]
         L.pfb_bank_last_launch.restype = ci
+        L.pfb_bank_timing_begin.argtypes = [vp, ci]
+        L.pfb_bank_timing_begin.restype = ci
+        L.pfb_bank_timing_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
+        L.pfb_bank_timing_end.restype = ci
         L.pfb_bank_set_warm_tol.argtypes = [vp, ctypes.c_double]
         L.pfb_bank_set_warm_tol.restype = ci
         L.pfb_fos_bank_c128.argtypes = [vp, i64, vp, i64, vp, ci, ci, vp, i64, ci, vp]
@@ -116,6 +120,16 @@ class Bank:
     def set_warm_tol(self, tol):
         """Relative-L2 budget of the truncated pre-pass of the time-chunked kernel (0: exact)."""
         check(lib().pfb_bank_set_warm_tol(self._h, float(tol)))
+
+    def timing_begin(self, max_calls):
+        check(lib().pfb_bank_timing_begin(self._h, int(max_calls)))
+
+    def timing_end(self):
+        """Mean device ms per call: {prepass, carry, output, total, calls} since timing_begin."""
+        ms = (ctypes.c_double * 4)()
+        calls = ctypes.c_int()
+        check(lib().pfb_bank_timing_end(self._h, ms, ctypes.byref(calls)))
+        return {"prepass": ms[0], "carry": ms[1], "output": ms[2], "total": ms[3], "calls": calls.value}
 
     def last_launch(self):
         info = LaunchInfo()

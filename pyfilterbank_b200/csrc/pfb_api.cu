@@ -17,6 +17,7 @@
 
 #include "../../include/pfb_sos.h"
 #include "pfb_kernels.cuh"
+#include "pfb_tma.cuh"
 
 namespace {
 
@@ -49,6 +50,7 @@ struct Sweep {
 
 struct Tables {          // device tables of one (arithmetic type, chunk length)
     std::vector<void *> P;    // per sweep: [rows][2K][2K]
+    double *gains = nullptr;  // [rows][K][2] = (G_k, 1/G_k) of the gain-normalised arithmetic, or null
     std::vector<int *> warm;  // per sweep: [rows] or null
     long long warm_total = 0;
 };
@@ -66,12 +68,28 @@ struct pfb_bank {
     std::vector<double> sos;  // [rows][K][6]
     void *coef[2] = {nullptr, nullptr};   // [PFB_F32 / PFB_F64] device [rows][K][5]
     std::vector<double> coef_host;        // [rows][K][5] = b0 b1 b2 a1 a2
+    std::map<void *, std::pair<void *, size_t>> workspace;   // per stream: chunk-state scratch of the TMA path
     std::vector<Sweep> sweeps;
     std::map<std::tuple<int, long long>, Tables> tables;
     std::mutex mu;
     pfb_launch_info last{};
     int sm_count = 148;
     double warm_tol = 1e-11;   // relative L2 budget of the truncated pre-pass (0: always exact)
+    // pfb_bank_timing_begin / _end: event pairs recorded around the kernels of the next `timing_left` calls
+    struct TimeRec { cudaEvent_t a, b; int kind; };   // kind 0 pre-pass, 1 carry, 2 output pass, 3 whole call
+    std::vector<TimeRec> trecs;
+    std::vector<cudaEvent_t> tevents;
+    int timing_left = 0, timing_calls = 0;
+    // channel-group pipeline of the TMA path: pre-pass kernels on s_lo, carry + output pass on s_hi
+    cudaStream_t s_lo = nullptr, s_hi = nullptr;
+    std::vector<cudaEvent_t> pipe_ev;
+
+    cudaEvent_t tev_new() {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        tevents.push_back(e);
+        return e;
+    }
 };
 
 namespace {
@@ -197,6 +215,7 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
         for (auto &kv : b->tables) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
+            cudaFree(kv.second.gains);
         }
         b->tables.clear();
     }
@@ -243,6 +262,25 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
         }
         t.P.push_back(d);
     }
+    // gain tables of the normalised float64 arithmetic (single-sweep banks with well-scaled b0 only)
+    if (arith == PFB_F64 && b->sweeps.size() == 1 && !env_int("PFB_NO_SCALED", 0)) {
+        std::vector<double> g((size_t)b->rows * b->K * 2);
+        bool ok = true;
+        for (int r = 0; r < b->rows && ok; ++r) {
+            double G = 1.0;
+            for (int k = 0; k < b->K; ++k) {
+                g[((size_t)r * b->K + k) * 2] = G;
+                g[((size_t)r * b->K + k) * 2 + 1] = 1.0 / G;
+                G *= b->coef_host[((size_t)r * b->K + k) * 5];
+                const double m = std::fabs(G);
+                if (!(m > 1e-200 && m < 1e200)) ok = false;
+            }
+        }
+        if (ok) {
+            PFB_CUDA(cudaMalloc((void **)&t.gains, g.size() * sizeof(double)));
+            PFB_CUDA(cudaMemcpy(t.gains, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
     auto ins = b->tables.emplace(key, std::move(t));
     *out = &ins.first->second;
     return PFB_OK;
@@ -264,6 +302,38 @@ std::vector<Sweep> split_sweeps(int K) {
 }
 
 bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// rows x chunks x time view of a [rows][ld] signal cut into J chunks of L samples; box = 32 chunks x
+// one 128-byte half row, 128-byte swizzle (chunk c of row r at c ^ (r & 7), the layout filter_half reads)
+bool make_chunk_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long rows, long long ld) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t esz = dtype == PFB_F64 ? 8 : 4;
+    cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)J, (cuuint64_t)rows};
+    cuuint64_t strides[2] = {(cuuint64_t)L * esz, (cuuint64_t)ld * esz};
+    cuuint32_t box[3] = {(cuuint32_t)(pfb::kRowBytes / esz), 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, dtype == PFB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
 
 }  // namespace
 
@@ -315,9 +385,15 @@ void pfb_bank_destroy(pfb_bank *b) {
     if (!b) return;
     for (int i = 0; i < 2; ++i)
         if (b->coef[i]) cudaFree(b->coef[i]);
+    for (auto &kv : b->workspace) cudaFree(kv.second.first);
+    for (cudaEvent_t e : b->tevents) cudaEventDestroy(e);
+    for (cudaEvent_t e : b->pipe_ev) cudaEventDestroy(e);
+    if (b->s_lo) cudaStreamDestroy(b->s_lo);
+    if (b->s_hi) cudaStreamDestroy(b->s_hi);
     for (auto &kv : b->tables) {
         for (void *p : kv.second.P) cudaFree(p);
         for (int *p : kv.second.warm) cudaFree(p);
+        cudaFree(kv.second.gains);
     }
     delete b;
 }
@@ -330,10 +406,43 @@ int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
         for (auto &kv : b->tables) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
+            cudaFree(kv.second.gains);
         }
         b->tables.clear();
         b->warm_tol = tol;
     }
+    return PFB_OK;
+}
+
+int pfb_bank_timing_begin(pfb_bank *b, int max_calls) {
+    if (!b || max_calls < 0) return fail(PFB_ERR_INVALID, "pfb_bank_timing_begin: bad argument");
+    std::lock_guard<std::mutex> lock(b->mu);
+    PFB_CUDA(cudaDeviceSynchronize());
+    for (cudaEvent_t e : b->tevents) cudaEventDestroy(e);
+    b->tevents.clear();
+    b->trecs.clear();
+    b->timing_left = max_calls;
+    b->timing_calls = 0;
+    return PFB_OK;
+}
+
+int pfb_bank_timing_end(pfb_bank *b, double *ms, int *calls) {
+    if (!b || !ms || !calls) return fail(PFB_ERR_INVALID, "pfb_bank_timing_end: null argument");
+    std::lock_guard<std::mutex> lock(b->mu);
+    for (int i = 0; i < 4; ++i) ms[i] = 0;
+    *calls = b->timing_calls;
+    for (const pfb_bank::TimeRec &r : b->trecs) {
+        PFB_CUDA(cudaEventSynchronize(r.b));
+        float t;
+        PFB_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.kind] += t;
+    }
+    if (b->timing_calls > 0)
+        for (int i = 0; i < 4; ++i) ms[i] /= b->timing_calls;
+    for (cudaEvent_t e : b->tevents) cudaEventDestroy(e);
+    b->tevents.clear();
+    b->trecs.clear();
+    b->timing_left = b->timing_calls = 0;
     return PFB_OK;
 }
 
@@ -395,6 +504,159 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     int warps = 1;
     long long L = n;
     const Tables *tab = nullptr;
+    // TMA variant of the time-chunked path (pfb_tma.cuh): shared-input banks, one sweep, 16-byte aligned rows
+    if (mode == PFB_MODE_SCAN && !(flags & 0x100) && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
+        !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 && (ldy * esz) % 16 == 0 &&
+        b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections)) {
+        const int tt = 2 * tlen;
+        int nbmax = env_int("PFB_TMA_NB", pfb::kTmaSmallBands);
+        nbmax = std::max(1, std::min(nbmax, pfb::kTmaMaxBands));
+        const int G0 = (b->B + nbmax - 1) / nbmax;
+        const int nb = (b->B + G0 - 1) / G0;
+        const int G = (b->B + nb - 1) / nb;
+        // chunk groups: fill whole waves of CTAs (2 resident per SM) while keeping chunks long
+        int groups = env_int("PFB_TMA_GROUPS", 0);
+        if (groups <= 0) {
+            double best = -1;
+            const double slots = 2.0 * b->sm_count;
+            for (int g = 1; g <= 8; ++g) {
+                if (n / (32LL * g) < 64LL * tt && g > 1) break;
+                const double waves = (double)C * G * g / slots;
+                const double eff = waves / std::ceil(waves) - 0.01 * g;   // prefer longer chunks at equal fill
+                if (eff > best) best = eff, groups = g;
+            }
+        }
+        const int J = 32 * groups;
+        const long long Lt = n / J / tt * tt;
+        if (Lt >= 4LL * tt && Lt < 0x7fffffffLL) {
+            rc = ensure_tables(b, arith, Lt, &tab);
+            if (rc) return rc;
+            const long long n_main = Lt * J;
+            CUtensorMap xmap, ymap;
+            if (make_chunk_map(&xmap, dtype, x, Lt, J, C, ldx) && make_chunk_map(&ymap, dtype, y, Lt, J, Qll, ldy)) {
+                const size_t asz = arith64 ? 8 : 4;
+                // chunk-state scratch: kept per (bank, stream) so repeated calls do not allocate
+                const size_t need = (size_t)Q * J * 2 * b->K * asz;
+                auto &ws = b->workspace[(void *)stream];
+                if (ws.second < need) {
+                    if (ws.first) {
+                        PFB_CUDA(cudaStreamSynchronize(stream));
+                        cudaFree(ws.first);
+                        ws = {nullptr, 0};
+                    }
+                    PFB_CUDA(cudaMalloc(&ws.first, need));
+                    ws.second = need;
+                }
+                void *zs = ws.first;
+                const bool timed = b->timing_left > 0;
+                if (timed) { --b->timing_left; ++b->timing_calls; }
+                // Channel groups: the pre-pass of group g+1 (FP64-pipe bound, almost no DRAM traffic) runs on a
+                // low-priority stream beside the output pass of group g (DRAM bound) on a high-priority one.
+                int NG = env_int("PFB_TMA_CGROUPS", 0);
+                if (NG <= 0) NG = C >= 32 ? 8 : C >= 8 ? C / 4 : 1;
+                NG = std::max(1, std::min(NG, std::min(C, 64)));
+                if (NG > 1 && !b->s_lo) {
+                    int lo = 0, hi = 0;
+                    PFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    PFB_CUDA(cudaStreamCreateWithPriority(&b->s_lo, cudaStreamNonBlocking, lo));
+                    PFB_CUDA(cudaStreamCreateWithPriority(&b->s_hi, cudaStreamNonBlocking, hi));
+                }
+                while ((int)b->pipe_ev.size() < NG + 2) {
+                    cudaEvent_t e = nullptr;
+                    PFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    b->pipe_ev.push_back(e);
+                }
+                cudaStream_t s_a = NG > 1 ? b->s_lo : stream, s_b = NG > 1 ? b->s_hi : stream;
+                cudaEvent_t t_fork = nullptr;
+                if (timed) {
+                    t_fork = b->tev_new();
+                    PFB_CUDA(cudaEventRecord(t_fork, stream));
+                }
+                if (NG > 1) {
+                    PFB_CUDA(cudaEventRecord(b->pipe_ev[NG], stream));
+                    PFB_CUDA(cudaStreamWaitEvent(s_a, b->pipe_ev[NG], 0));
+                    PFB_CUDA(cudaStreamWaitEvent(s_b, b->pipe_ev[NG], 0));
+                }
+                int launches = 0;
+                const double *ch = b->coef_host.data();
+                const size_t asz_state = (size_t)b->B * b->K * 2 * asz;
+                for (int g = 0; g < NG; ++g) {
+                    const int c0 = (int)((long long)C * g / NG), c1 = (int)((long long)C * (g + 1) / NG);
+                    const int Cg = c1 - c0;
+                    if (Cg <= 0) continue;
+                    const char *xg = (const char *)x + (size_t)c0 * ldx * esz;
+                    char *yg = (char *)y + (size_t)c0 * b->B * ldy * esz;
+                    CUtensorMap xmap, ymap;
+                    if (!make_chunk_map(&xmap, dtype, xg, Lt, J, Cg, ldx) ||
+                        !make_chunk_map(&ymap, dtype, yg, Lt, J, (long long)Cg * b->B, ldy))
+                        return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+                    pfb::TmaParams tp{};
+                    tp.zs = (char *)zs + (size_t)c0 * b->B * J * 2 * b->K * asz;
+                    tp.P = tab->P[0];
+                    tp.states = (char *)states + (size_t)c0 * asz_state;
+                    tp.warm = tab->warm[0];
+                    tp.L = Lt;
+                    tp.Q = Cg * b->B, tp.B = b->B, tp.C = Cg, tp.J = J, tp.nb = nb, tp.G = G;
+                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", nb), nb));
+                    tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
+                    tp.Ktot = b->K, tp.k0 = 0;
+                    tp.gains = tab->gains;
+                    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, t_c0 = nullptr;
+                    if (timed) {
+                        for (cudaEvent_t &e : ev) e = b->tev_new();
+                        t_c0 = b->tev_new();
+                    }
+                    for (int phase = 1; phase <= 2; ++phase) {
+                        cudaStream_t sp = phase == 1 ? s_a : s_b;
+                        if (phase == 2) {
+                            if (NG > 1) {
+                                PFB_CUDA(cudaEventRecord(b->pipe_ev[g], s_a));
+                                PFB_CUDA(cudaStreamWaitEvent(s_b, b->pipe_ev[g], 0));
+                            }
+                            if (timed) PFB_CUDA(cudaEventRecord(t_c0, s_b));
+                        }
+                        int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase)
+                                  : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase)
+                                                  : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase);
+                        if (err != 0)
+                            return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+                    }
+                    if (timed) {
+                        b->trecs.push_back({ev[0], ev[1], 0});
+                        b->trecs.push_back({t_c0, ev[2], 1});
+                        b->trecs.push_back({ev[2], ev[3], 2});
+                    }
+                }
+                if (NG > 1) {
+                    PFB_CUDA(cudaEventRecord(b->pipe_ev[NG + 1], s_b));
+                    PFB_CUDA(cudaStreamWaitEvent(stream, b->pipe_ev[NG + 1], 0));
+                }
+                if (timed) {
+                    cudaEvent_t t_join = b->tev_new();
+                    PFB_CUDA(cudaEventRecord(t_join, stream));
+                    b->trecs.push_back({t_fork, t_join, 3});
+                }
+                pfb_launch_info main_info{};
+                main_info.mode = PFB_MODE_SCAN;
+                main_info.kernels = launches;
+                main_info.warps_per_cascade = groups;
+                main_info.chunk = Lt;
+                main_info.warm_total = tab->warm_total * C;
+                main_info.aligned = 2;   // 2 = TMA path
+                if (n_main < n) {        // the ragged end continues from the carried states
+                    b->mu.unlock();
+                    rc = pfb_bank_filter(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
+                                         states, n - n_main, C, (flags & ~PFB_MODE_MASK) | 0x100 | PFB_MODE_AUTO, stream_);
+                    b->mu.lock();
+                    if (rc) return rc;
+                    main_info.kernels += b->last.kernels;
+                }
+                b->last = main_info;
+                g_status = PFB_OK;
+                return PFB_OK;
+            }
+        }
+    }
     if (mode == PFB_MODE_SCAN) {
         const long long want_warps = (long long)b->sm_count * 16;
         warps = env_int("PFB_SCAN_WARPS", 0);
@@ -422,6 +684,13 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     p.per_channel = b->per_channel;
     p.Ktot = b->K;
     int launches = 0;
+    cudaEvent_t t0 = nullptr;
+    if (!(flags & 0x100) && b->timing_left > 0) {   // single-kernel paths: all time is booked on the output pass
+        --b->timing_left;
+        ++b->timing_calls;
+        t0 = b->tev_new();
+        cudaEventRecord(t0, stream);
+    }
     for (size_t si = 0; si < b->sweeps.size(); ++si) {
         const Sweep &sw = b->sweeps[si];
         p.k0 = sw.k0;
@@ -451,6 +720,12 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
         if (err != 0)
             return fail(PFB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
         if (mode == PFB_MODE_SEQ) ++launches;
+    }
+    if (t0) {
+        cudaEvent_t t1 = b->tev_new();
+        cudaEventRecord(t1, stream);
+        b->trecs.push_back({t0, t1, 2});
+        b->trecs.push_back({t0, t1, 3});
     }
     b->last.mode = mode;
     b->last.kernels = launches;

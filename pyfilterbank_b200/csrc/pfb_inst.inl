@@ -1,8 +1,10 @@
 // pfb_inst.inl -- kernel instantiations and launchers for one (signal type, arithmetic type) pair.
 // Included by pfb_inst_{dd,ff,fd}.cu with PFB_T, PFB_A and PFB_SUFFIX defined.
+#include <cstdlib>
 #include <vector>
 
 #include "pfb_kernels.cuh"
+#include "pfb_tma.cuh"
 
 #define PFB_CAT2(a, b) a##b
 #define PFB_CAT(a, b) PFB_CAT2(a, b)
@@ -57,6 +59,65 @@ static int run_scan(const SosParams &p, int warps, const double *coef_host, int 
                      : run_scan_a<K, false>(p, warps, coef_host, rows, C, s, launches);
 }
 
+template <int K, int NBMAX, bool SCALED>
+static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                      cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, false, NBMAX, SCALED>;
+    auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, true, NBMAX, SCALED>;
+    const int smem_a = kTmaStages * 2 * kTileBytes + 2 * kTmaStages * 8;
+    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 2 * kTmaStages * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+    if (e != cudaSuccess) return (int)e;
+    static thread_local CoefTable<PFB_A> tab;
+    for (int r = 0; r < p.B; ++r) {
+        double total_gain = 1.0;
+        for (int k = 0; k < K; ++k) {
+            const double *c = &coef_host[((size_t)r * p.Ktot + p.k0 + k) * 5];
+            for (int i = 0; i < 5; ++i) tab.c[r * K + k][i] = (PFB_A)c[i];
+            if (SCALED) {   // numerator normalised by b0: (., b1/b0, b2/b0)
+                tab.c[r * K + k][1] = (PFB_A)(c[1] / c[0]);
+                tab.c[r * K + k][2] = (PFB_A)(c[2] / c[0]);
+                total_gain *= c[0];
+            }
+        }
+        if (SCALED) tab.c[r * K][0] = (PFB_A)total_gain;
+    }
+    constexpr int S = 2 * K;
+    constexpr int LPC = S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16;
+    const unsigned grid = (unsigned)p.C * (unsigned)p.G * (unsigned)(p.J / 32);
+    const unsigned grid_a = (unsigned)p.C * (unsigned)p.G_a * (unsigned)(p.J / 32);
+    const int threads = (p.nb + 1) * 32;
+    if (phases & 1) {
+        if (ev) cudaEventRecord(ev[0], s);
+        kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap);
+        if (ev) cudaEventRecord(ev[1], s);
+        *launches += 1;
+    }
+    if (phases & 2) {
+        sos_carry_kernel<PFB_A, K><<<(unsigned)(((long long)p.Q * LPC + 127) / 128), 128, 0, s>>>(p);
+        if (ev) cudaEventRecord(ev[2], s);
+        kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+        if (ev) cudaEventRecord(ev[3], s);
+        *launches += 2;
+    }
+    return (int)cudaGetLastError();
+}
+template <int K, int NBMAX>
+static int run_tma_n(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                     cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+#if PFB_HAS_SCALED
+    if (p.gains) return run_tma_ns<K, NBMAX, true>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+#endif
+    return run_tma_ns<K, NBMAX, false>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+}
+template <int K>
+static int run_tma(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                   cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    return p.nb <= kTmaSmallBands ? run_tma_n<K, kTmaSmallBands>(p, coef_host, xmap, ymap, s, launches, ev, phases)
+                                  : run_tma_n<K, kTmaMaxBands>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+}
+
 #define PFB_K_SWITCH(CALL)                          \
     switch (K) {                                    \
         case 1: return CALL(1);                     \
@@ -81,6 +142,12 @@ int PFB_CAT(launch_scan_, PFB_SUFFIX)(SosParams p, int K, int warps, const doubl
                                       cudaStream_t s, int *launches) {
 #define PFB_SCAN(k) run_scan<k>(p, warps, coef_host, rows, C, s, launches)
     PFB_K_SWITCH(PFB_SCAN)
+}
+
+int PFB_CAT(launch_tma_, PFB_SUFFIX)(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap,
+                                     const CUtensorMap &ymap, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+#define PFB_TMA(k) run_tma<k>(p, coef_host, xmap, ymap, s, launches, ev, phases)
+    PFB_K_SWITCH(PFB_TMA)
 }
 
 }  // namespace pfb

@@ -3,4 +3,5 @@
 #define PFB_A double
 #define PFB_SUFFIX dd
 #define PFB_HAS_EXACT true   // the exact (reference rounding) variant only exists when T == A
+#define PFB_HAS_SCALED 1   // gain-normalised TMA kernels need float64 arithmetic
 #include "pfb_inst.inl"

@@ -3,4 +3,5 @@
 #define PFB_A double
 #define PFB_SUFFIX fd
 #define PFB_HAS_EXACT false   // the exact (reference rounding) variant only exists when T == A
+#define PFB_HAS_SCALED 1   // gain-normalised TMA kernels need float64 arithmetic
 #include "pfb_inst.inl"

@@ -3,4 +3,5 @@
 #define PFB_A float
 #define PFB_SUFFIX ff
 #define PFB_HAS_EXACT true   // the exact (reference rounding) variant only exists when T == A
+#define PFB_HAS_SCALED 0   // gain-normalised TMA kernels need float64 arithmetic
 #include "pfb_inst.inl"

@@ -1,0 +1,348 @@
+// pfb_tma.cuh -- TMA / mbarrier variant of the time-chunked SOS bank for shared-input banks.
+//
+// Why a second scan kernel: profiling the cp.async kernel (profiles/) showed it bound by DRAM
+// traffic of scattered 128-byte rows -- every (channel, band) CTA re-read the channel's input, and
+// rows of 128 bytes reach only ~3.9 TB/s on B200 where 256-byte rows reach ~5.5 TB/s
+// (scripts/ubench/stream_rows.cu).  Here
+//   * one CTA owns one channel, one time chunk group (32 chunks) and a GROUP of bands: a producer
+//     warp streams the channel's input tiles [32 chunks x 32 samples] into a shared-memory ring with
+//     TMA (cp.async.bulk.tensor, 128-byte swizzle, mbarrier complete_tx) and every band warp of the
+//     CTA reads them from there, so the input is fetched once per band group instead of once per band;
+//   * every band warp filters its lane's row in registers and hands its [32 x 256-byte] output tile
+//     to TMA stores, so no thread spends instructions on global addressing and HBM sees 256-byte rows;
+//   * the work is split into three launches whose CTAs are all independent (pre-pass A, carry, output
+//     pass B), so the hardware scheduler balances the band-dependent pre-pass cost over the 148 SMs.
+// The arithmetic, the chunk-transition carry and the truncated pre-pass are the ones of
+// sos_scan_kernel (pfb_kernels.cuh); states and outputs are identical up to the chunk length.
+#pragma once
+#include <cuda.h>
+
+#include "pfb_kernels.cuh"
+
+namespace pfb {
+
+constexpr int kTmaStages = 3;
+constexpr int kTmaMaxBands = 11;               // most band (consumer) warps per CTA; +1 producer warp
+constexpr int kTmaSmallBands = 7;              // CTA shape with 112 registers per thread (no spills for K <= 6)
+
+struct TmaParams {
+    void *zs;             // [Q][J][2K] arithmetic type: pre-pass states, then chunk start states
+    const void *P;        // [B][2K][2K]
+    void *states;         // [Q][Ktot][2]
+    const int *warm;      // [B]
+    long long L;          // chunk length, multiple of the tile time length
+    int Q, B, C;
+    int J;                // chunks per cascade = 32 * groups
+    int nb;               // band warps per CTA (output pass)
+    int G;                // band groups = ceil(B / nb)
+    int nb_a, G_a;        // the same for the pre-pass, whose CTAs are smaller: bands of one CTA should
+                          // have similar pre-pass lengths, or their warps idle while the longest one runs
+    int Ktot, k0;
+    // Gain-normalised arithmetic (float64 only): section k runs on states scaled by 1 / (b0_0 ... b0_{k-1})
+    // with numerator (1, b1/b0, b2/b0), which saves the multiply by b0 in every section (17 instead of
+    // 20 FP64 operations per band sample for 4 sections; the product of the gains is applied once at
+    // the output).  gains [B][K][2] = (G_k, 1 / G_k), G_k = b0_0 ... b0_{k-1}; null: plain arithmetic.
+    const double *gains;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
+            "r"(smem_addr(dst)),
+        "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(map),
+                 "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// One section in gain-normalised form: c = {total gain (section 0 only), b1/b0, b2/b0, a1, a2}.
+template <typename A>
+__device__ __forceinline__ A scaled_step(A x, const A *c, A &w1, A &w2) {
+    const A t = fma(-c[4], w2, x);
+    const A w0 = fma(-c[3], w1, t);
+    const A y = fma(c[2], w2, fma(c[1], w1, w0));
+    w2 = w1;
+    w1 = w0;
+    return y;
+}
+
+// Filter one 128-byte half tile: x row read from the shared input tile, result written to the warp's
+// own output tile (same swizzled layout).  STORE = false: pre-pass, nothing is written.
+template <typename T, typename A, int K, bool STORE, bool SCALED>
+__device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int key, const A (&c)[K][5], A (&w)[K][2]) {
+    using V = typename Vec16<T>::type;
+    constexpr int EPV = Vec16<T>::N;
+    constexpr int kBatch = PFB_ROW_BATCH;
+#pragma unroll
+    for (int v0 = 0; v0 < kVecPerRow; v0 += kBatch) {
+        V in[kBatch];
+#pragma unroll
+        for (int v = 0; v < kBatch; ++v) in[v] = *reinterpret_cast<const V *>(xrow + (((v0 + v) ^ key) << 4));
+#pragma unroll
+        for (int v = 0; v < kBatch; ++v) {
+            T *e = reinterpret_cast<T *>(&in[v]);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                A s = (A)e[i];
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    s = SCALED ? scaled_step<A>(s, c[k], w[k][0], w[k][1]) : Biquad<A, false>::step(s, c[k], w[k][0], w[k][1]);
+                if (SCALED) s *= c[0][0];
+                e[i] = (T)s;
+            }
+        }
+        if (STORE) {
+#pragma unroll
+            for (int v = 0; v < kBatch; ++v) *reinterpret_cast<V *>(yrow + (((v0 + v) ^ key) << 4)) = in[v];
+        }
+    }
+}
+
+// cta = ((c * G) + g) * groups + w   (groups = J / 32), c counted from ch0
+// PASS_B = false: pre-pass, writes zero-state chunk end states to zs; true: output pass from zs.
+template <typename T, typename A, int K, bool PASS_B, bool SCALED>
+__device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
+                                        const CUtensorMap &ymap, char *smem, int cta, int ch0) {
+    constexpr int TLEN = kRowBytes / (int)sizeof(T);      // samples per 128-byte half row
+    constexpr int TT = 2 * TLEN;                          // samples per tile step (256-byte rows)
+    constexpr int S = 2 * K;
+    constexpr unsigned kStageBytes = 2 * kTileBytes;
+    const int lane = threadIdx.x & 31, key = lane & 7;
+    // warp index through a warp reduction: the result lives in a uniform register, so everything
+    // indexed by it (the band's coefficients) can stay in uniform registers -- DFMA R, R, UR, R reads
+    // two register pairs instead of three and issues at full FP64 rate
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int groups = p.J >> 5;
+    const int w = cta % groups;
+    const int cg = cta / groups;
+    const int nbw = PASS_B ? p.nb : p.nb_a, G = PASS_B ? p.G : p.G_a;
+    const int g = cg % G, ch = ch0 + cg / G;
+    const int b0 = g * nbw;
+    const int nb_here = min(nbw, p.B - b0);
+
+    char *xs = smem;                                          // [stages][2][tile]
+    char *ys = smem + kTmaStages * kStageBytes;               // [nb][2][tile], output pass only
+    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (PASS_B ? p.nb : 0) * kStageBytes);
+    uint64_t *empty = full + kTmaStages;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nb_here);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long nt = p.L / TT;
+    // first tile of the pre-pass: the longest pre-pass among this CTA's bands
+    long long t_first = 0;
+    if (!PASS_B) {
+        int wmax = 0;
+        for (int i = 0; i < nb_here; ++i) wmax = max(wmax, p.warm ? p.warm[b0 + i] : (int)min(p.L, 0x7fffffffLL));
+        long long wt = ((long long)wmax + TT - 1) / TT;
+        if (wt > nt) wt = nt;
+        t_first = nt - wt;
+    }
+
+    if (warp == nbw) {
+        // ---------------- producer: stream the channel's input tiles into the ring ----------------
+        if (lane == 0) {
+            for (long long t = t_first; t < nt; ++t) {
+                const long long it = t - t_first;
+                const int s = (int)(it % kTmaStages);
+                const unsigned ph = (unsigned)((it / kTmaStages) & 1);
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], kStageBytes);
+                char *dst = xs + s * kStageBytes;
+                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), 32 * w, ch);
+                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), 32 * w, ch);
+            }
+        }
+        return;
+    }
+    if (warp >= nb_here) return;
+
+    // ---------------- consumers: one band per warp, one chunk per lane ----------------
+    const int band = b0 + warp;
+    const int q = ch * p.B + band;
+    const int j = 32 * w + lane;
+    A c[K][5], wst[K][2];
+    // a second, independently reduced copy of the band index that is used for nothing but the
+    // coefficient table, so its users stay on the uniform datapath
+    const int band_u = b0 + __reduce_min_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c[k][i] = tab.c[band_u * K + k][i];
+    A *zs = reinterpret_cast<A *>(p.zs) + ((size_t)q * p.J + j) * S;
+    const double *gain = SCALED ? p.gains + (size_t)band * K * 2 : nullptr;
+    if (PASS_B) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            wst[k][0] = zs[2 * k];
+            wst[k][1] = zs[2 * k + 1];
+            if (SCALED) { wst[k][0] *= (A)gain[2 * k + 1]; wst[k][1] *= (A)gain[2 * k + 1]; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) wst[k][0] = wst[k][1] = A(0);
+    }
+    int t_mine = 0;
+    if (!PASS_B) {
+        // (reduced across the warp only so that the compiler sees a warp-uniform loop bound)
+        const int warm = __reduce_max_sync(0xffffffffu, p.warm ? p.warm[band] : 0x7fffffff);
+        long long wt = ((long long)warm + TT - 1) / TT;
+        if (wt > nt) wt = nt;
+        t_mine = (int)(nt - wt);
+    }
+    char *ybuf = ys + warp * kStageBytes;
+    char *yrow = ybuf + lane * kRowBytes;
+
+    if (PASS_B) {
+        for (long long t = 0; t < nt; ++t) {
+            const int s = (int)(t % kTmaStages);
+            const unsigned ph = (unsigned)((t / kTmaStages) & 1);
+            mbar_wait(&full[s], ph);
+            const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+            // the previous tile's TMA stores must have finished reading this warp's output buffer
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            filter_half<T, A, K, true, SCALED>(xrow, yrow, key, c, wst);
+            filter_half<T, A, K, true, SCALED>(xrow + kTileBytes, yrow + kTileBytes, key, c, wst);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                tma_store_3d(&ymap, ybuf, (int)(t * TT), 32 * w, q);
+                tma_store_3d(&ymap, ybuf + kTileBytes, (int)(t * TT + TLEN), 32 * w, q);
+                bulk_commit();
+            }
+        }
+    } else {
+        // tiles before this band's own pre-pass start are only released, not filtered
+        long long t = t_first;
+        for (; t < t_mine; ++t) {
+            const long long it = t - t_first;
+            const int s = (int)(it % kTmaStages);
+            mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        for (; t < nt; ++t) {
+            const long long it = t - t_first;
+            const int s = (int)(it % kTmaStages);
+            mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+            const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+            filter_half<T, A, K, false, SCALED>(xrow, nullptr, key, c, wst);
+            filter_half<T, A, K, false, SCALED>(xrow + kTileBytes, nullptr, key, c, wst);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (PASS_B) {
+        if (lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
+        if (j == p.J - 1) {              // the last chunk ends with the cascade's final state
+            A *st = reinterpret_cast<A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const A gk = SCALED ? (A)gain[2 * k] : A(1);
+                st[2 * k] = wst[k][0] * gk;
+                st[2 * k + 1] = wst[k][1] * gk;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const A gk = SCALED ? (A)gain[2 * k] : A(1);
+            zs[2 * k] = wst[k][0] * gk;
+            zs[2 * k + 1] = wst[k][1] * gk;
+        }
+    }
+}
+
+// The pre-pass needs no output tiles and few registers: it is compiled for 4 resident CTAs per SM
+// (which also makes ptxas keep the coefficients in uniform registers), the output pass for 2.
+template <typename T, typename A, int K, bool PASS_B, int NBMAX, bool SCALED>
+__global__ void __launch_bounds__((NBMAX + 1) * 32, PASS_B ? 2 : 4)
+sos_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
+               const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+    extern __shared__ __align__(1024) char smem[];
+    tma_cta<T, A, K, PASS_B, SCALED>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
+}
+
+// Carry between the two passes: per cascade, s[0] = carried-in state, s[j+1] = P s[j] + z[j];
+// zs[q][j] is overwritten with chunk j's initial state.  2K lanes per cascade (lane i owns row i of
+// P and component i of the state; the state vector is exchanged with shuffles), so the J
+// sequential steps cost one short dot product each and the zs accesses are contiguous.
+template <typename A, int K>
+__global__ void __launch_bounds__(128) sos_carry_kernel(const TmaParams p) {
+    constexpr int S = 2 * K;
+    constexpr int LPC = S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16;   // lanes per cascade (power of two)
+    constexpr int CPW = 32 / LPC;                                     // cascades per warp
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPC;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long q = warp * CPW + lane / LPC;
+    const bool active = q < p.Q && sub < S;
+    const long long qq = q < p.Q ? q : p.Q - 1;
+    const int band = (int)(qq % p.B);
+    const A *P = reinterpret_cast<const A *>(p.P) + (size_t)band * S * S;
+    const A *st = reinterpret_cast<const A *>(p.states) + ((size_t)qq * p.Ktot + p.k0) * 2;
+    A *zs = reinterpret_cast<A *>(p.zs) + (size_t)qq * p.J * S;
+    A prow[S];
+#pragma unroll
+    for (int m = 0; m < S; ++m) prow[m] = sub < S ? P[sub * S + m] : A(0);
+    A s = sub < S ? st[sub] : A(0);
+    const int base = lane - sub;
+    A znext = sub < S ? zs[sub] : A(0);
+    for (int j = 0; j < p.J; ++j) {
+        const A z = znext;
+        if (j + 1 < p.J && sub < S) znext = zs[(size_t)(j + 1) * S + sub];   // prefetch
+        if (active) zs[(size_t)j * S + sub] = s;
+        A acc = z;
+#pragma unroll
+        for (int m = 0; m < S; ++m) acc = fma(prow[m], __shfl_sync(0xffffffffu, s, base + m), acc);
+        s = acc;
+    }
+}
+
+// ev: null, or 4 events recorded before the pre-pass and after each of the three kernels
+// phases: 1 = pre-pass, 2 = carry + output pass, 3 = all (on stream s)
+int launch_tma_dd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+int launch_tma_ff(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+int launch_tma_fd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+
+}  // namespace pfb

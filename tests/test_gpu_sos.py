@@ -213,3 +213,56 @@ def test_f32_bank_modes(pfb, oracle):
             assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (mode, b, ref_err)
     y3, _ = pfb.bank_filter(bank, xt, mode="seq", exact=True)
     assert np.array_equal(y3.cpu().numpy(), yf)
+
+
+@pytest.mark.parametrize("scaled", [True, False])
+def test_tma_path_parity(pfb, oracle, scaled, monkeypatch):
+    """The TMA / mbarrier kernels (shared-input bank, 16-byte aligned rows, long signals): three
+    launches (pre-pass, carry, output pass) + a ragged tail, plain and gain-normalised arithmetic,
+    carried states over two calls."""
+    if not scaled:
+        monkeypatch.setenv("PFB_NO_SCALED", "1")
+    rng = np.random.default_rng(77)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    C, n = 3, 300000 + 4 * 13                      # not a multiple of the chunk grid: exercises the tail
+    x = rng.standard_normal((C, n))
+    st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+    y0, s0 = oracle.sos_bank(x, sos, st0)
+    bank = pfb.Bank(sos)                            # fresh bank: tables built under the env setting
+    xt = torch.from_numpy(x).cuda()
+    y1, s1 = pfb.bank_filter(bank, xt, torch.from_numpy(st0.copy()).cuda(), mode="scan")
+    assert bank.last_launch()["aligned"] == 2       # the TMA path ran
+    y1, s1 = y1.cpu().numpy(), s1.cpu().numpy()
+    worst = max(rel_l2(y1[:, b], y0[:, b]) for b in range(B))
+    assert worst <= TOL64, worst
+    assert rel_l2(s1, s0) <= 1e-8
+    # two blocks with carried states
+    cut = 163840
+    ya, st = pfb.bank_filter(bank, xt[:, :cut].contiguous(), torch.from_numpy(st0.copy()).cuda(), mode="scan")
+    yb, st = pfb.bank_filter(bank, xt[:, cut:].contiguous(), st, mode="scan")
+    y2 = torch.cat([ya, yb], dim=2).cpu().numpy()
+    assert max(rel_l2(y2[:, b], y0[:, b]) for b in range(B)) <= TOL64
+    assert rel_l2(st.cpu().numpy(), s0) <= 1e-8
+
+
+def test_tma_path_f32(pfb, oracle):
+    rng = np.random.default_rng(78)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    C, n = 2, 262144
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    yd, _ = oracle.sos_bank(x.astype(np.float64), sos)
+    yf, _ = oracle.sos_bank(x, sos.astype(np.float32), dtype=np.float32)
+    bank = pfb.Bank(sos)
+    xt = torch.from_numpy(x).cuda()
+    y1, _ = pfb.bank_filter(bank, xt, mode="scan", arith64=True)
+    assert bank.last_launch()["aligned"] == 2
+    y1 = y1.cpu().numpy()
+    for b in range(B):
+        assert rel_l2(y1[:, b], yd[:, b]) <= 1e-6, b
+    y2, _ = pfb.bank_filter(bank, xt, mode="scan")
+    y2 = y2.cpu().numpy()
+    for b in range(B):
+        ref_err = rel_l2(yf[:, b], yd[:, b])
+        assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (b, ref_err, rel_l2(y2[:, b], yd[:, b]))
