@@ -550,10 +550,11 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
                 void *zs = ws.first;
                 const bool timed = b->timing_left > 0;
                 if (timed) { --b->timing_left; ++b->timing_calls; }
-                // Channel groups: the pre-pass of group g+1 (FP64-pipe bound, almost no DRAM traffic) runs on a
-                // low-priority stream beside the output pass of group g (DRAM bound) on a high-priority one.
-                int NG = env_int("PFB_TMA_CGROUPS", 0);
-                if (NG <= 0) NG = C >= 32 ? 8 : C >= 8 ? C / 4 : 1;
+                // Channel groups (experimental, PFB_TMA_CGROUPS > 1): the pre-pass of group g+1 (FP64-pipe bound,
+                // almost no DRAM traffic) runs on a low-priority stream beside the output pass of group g
+                // (DRAM bound) on a high-priority one.  Measured on cfg 2 (gpurun_out sweep, profiles/): no gain,
+                // the two kernels slow each other down by as much as they overlap, so the default is one group.
+                int NG = env_int("PFB_TMA_CGROUPS", 1);
                 NG = std::max(1, std::min(NG, std::min(C, 64)));
                 if (NG > 1 && !b->s_lo) {
                     int lo = 0, hi = 0;

@@ -81,6 +81,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
@@ -235,7 +236,10 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const unsigned ph = (unsigned)((t / kTmaStages) & 1);
             mbar_wait(&full[s], ph);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            // the previous tile's TMA stores must have finished reading this warp's output buffer
+            // the previous tile's TMA stores must have finished reading this warp's output buffer.
+            // (Storing each 128-byte half as soon as it is filtered was measured and is slower: HBM write
+            // efficiency of this scattered-row pattern drops from ~5.0 to ~4.4 TB/s when a row's 256 bytes
+            // arrive as two separate 128-byte bursts; see profiles/r01_ubench_tma_store_rows.txt.)
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
             filter_half<T, A, K, true, SCALED>(xrow, yrow, key, c, wst);
