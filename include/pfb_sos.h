@@ -52,6 +52,10 @@ typedef enum pfb_status {
 #define PFB_EXACT 0x10      /* no FMA contraction, the reference's operation order: with PFB_MODE_SEQ the
                                result is bit-identical to sosfilt.c */
 #define PFB_ARITH_F64 0x20  /* float32 signals, float64 coefficients/states/arithmetic */
+#define PFB_DECIMATE2 0x40  /* store only every second output sample: y rows hold (n - phase + 1) / 2 samples,
+                               output i = filtered sample 2 i + phase (the anti-alias stage of the decimating
+                               band path; banks with K in {1,2,3,4,6,8} only) */
+#define PFB_DEC_PHASE1 0x80 /* phase = 1 (default 0): the block starts on an odd sample of the decimator */
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Reference drop-ins: the three symbols pyfilterbank/build.py:5-7 declares and

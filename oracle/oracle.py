@@ -191,3 +191,39 @@ def lfilter_df2t(b, a, x, zi=None):
     z = np.zeros(max(nt - 1, 1)) if zi is None else np.array(zi, np.float64)
     lib().oracle_tf_df2t_f64(_p(x, _f64p), _p(y, _f64p), x.shape[0], _p(bb, _f64p), _p(aa, _f64p), nt, _p(z, _f64p))
     return y, z
+
+
+# ---------------------------------------------------------------------------------------------
+# Composed paths (no single reference function exists; composed from the pieces above exactly like
+# tests/golden/make_golden_composed.py composes the reference's own functions).
+# ---------------------------------------------------------------------------------------------
+
+def decimated_bank(x, plan, aa_sos, order):
+    """Decimating band path: x (N, C); plan = list of stages {'m', 'bands', 'sosmat'} (stage 0 first);
+    stage m signal = [::2] of the anti-alias cascade `aa_sos` applied to the stage m-1 signal
+    (sosfilter_double arithmetic).  Returns a list over bands of (N_b, C) arrays."""
+    x = np.asarray(x, np.float64).reshape(len(x), -1)
+    C = x.shape[1]
+    nb = sum(len(s['bands']) for s in plan)
+    out = [None] * nb
+    for c in range(C):
+        stage = x[:, c].copy()
+        for st in plan:
+            if st['m'] > 0:
+                stage, _ = sosfilter_double_c(stage, aa_sos)
+                stage = stage[::2].copy()
+            for j, b in enumerate(st['bands']):
+                y, _ = sosfilter_double_c(stage, st['sosmat'][:, j].reshape(order, 6))
+                if out[b] is None:
+                    out[b] = np.zeros((len(y), C))
+                out[b][:, c] = y
+    return out
+
+
+def weighted_bank(x, b, a, sosmat):
+    """lfilter(b, a, .) per channel (splweighting.py:80) followed by sosfilter_double_mimo_c
+    (octbank.py:412-434).  x (N, C) -> (weighted (N, C), out (N, B, C), states flat)."""
+    x = np.asarray(x, np.float64).reshape(len(x), -1)
+    w = np.stack([lfilter_df2t(b, a, x[:, c])[0] for c in range(x.shape[1])], axis=1)
+    y, st = sosfilter_double_mimo_c(w, sosmat)
+    return w, y, st

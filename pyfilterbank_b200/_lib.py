@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libpfb_sos.so")
 
 PFB_F32, PFB_F64 = 0, 1
 MODE_AUTO, MODE_SEQ, MODE_SCAN = 0, 1, 2
-EXACT, ARITH_F64 = 0x10, 0x20
+EXACT, ARITH_F64, DECIMATE2, DEC_PHASE1 = 0x10, 0x20, 0x40, 0x80
 _MODES = {"auto": MODE_AUTO, "seq": MODE_SEQ, "scan": MODE_SCAN}
 
 
@@ -73,12 +73,14 @@ def check(rc):
         raise PfbError("libpfb_sos error %d: %s" % (rc, lib().pfb_last_error().decode()))
 
 
-def flags_of(mode="auto", exact=False, arith64=False):
+def flags_of(mode="auto", exact=False, arith64=False, decimate=None):
     f = _MODES[mode]
     if exact:
         f |= EXACT
     if arith64:
         f |= ARITH_F64
+    if decimate is not None:          # phase 0 / 1 of the decimate-by-2 store
+        f |= DECIMATE2 | (DEC_PHASE1 if decimate else 0)
     return f
 
 

@@ -461,9 +461,14 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     }
     if (!x || !y || !states) return fail(PFB_ERR_INVALID, "pfb_bank_filter: null argument");
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad dtype %d", dtype);
-    if (n < 0 || C <= 0 || ldx < n || ldy < n)
+    const bool dec = (flags & PFB_DECIMATE2) != 0;
+    const int dec_phase = (flags & PFB_DEC_PHASE1) ? 1 : 0;
+    const long long n_out = dec ? (n - dec_phase + 1) / 2 : n;
+    if (n < 0 || C <= 0 || ldx < n || ldy < n_out)
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad sizes n=%lld C=%d ldx=%lld ldy=%lld", (long long)n, C,
                     (long long)ldx, (long long)ldy);
+    if (dec && b->sweeps.size() != 1)
+        return fail(PFB_ERR_INVALID, "pfb_bank_filter: PFB_DECIMATE2 needs K in {1,2,3,4,6,8}, bank has K=%d", b->K);
     if (b->per_channel && C != b->C_sos)
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: bank holds per-channel coefficients for %d channels, got C=%d",
                     b->C_sos, C);
@@ -480,7 +485,7 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     if (exact && mode == PFB_MODE_SCAN)
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: PFB_EXACT needs PFB_MODE_SEQ (the scan re-associates)");
     const bool in_place = (const void *)x == (const void *)y;
-    if (in_place && (b->B != 1 || ldx != ldy))
+    if (in_place && (b->B != 1 || ldx != ldy || dec))
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: x may alias y only for single-band banks with ldx == ldy");
 
     std::lock_guard<std::mutex> lock(b->mu);
@@ -505,7 +510,7 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     long long L = n;
     const Tables *tab = nullptr;
     // TMA variant of the time-chunked path (pfb_tma.cuh): shared-input banks, one sweep, 16-byte aligned rows
-    if (mode == PFB_MODE_SCAN && !(flags & 0x100) && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
+    if (mode == PFB_MODE_SCAN && !(flags & 0x100) && !dec && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
         !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 && (ldy * esz) % 16 == 0 &&
         b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections)) {
         const int tt = 2 * tlen;
@@ -684,6 +689,8 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     p.B = b->B;
     p.per_channel = b->per_channel;
     p.Ktot = b->K;
+    p.dec = dec ? 1 : 0;
+    p.dec_phase = dec_phase;
     int launches = 0;
     cudaEvent_t t0 = nullptr;
     if (!(flags & 0x100) && b->timing_left > 0) {   // single-kernel paths: all time is booked on the output pass
@@ -748,6 +755,7 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
     if (!x || !y || !states) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: null argument");
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: bad dtype");
     if (n < 0 || C <= 0 || ldx < n || ldy < n) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: bad sizes");
+    if (flags & PFB_DECIMATE2) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: PFB_DECIMATE2 is a device-pointer option");
     const size_t esz = dtype == PFB_F64 ? 8 : 4;
     const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
     const long long Q = (long long)C * b->B;

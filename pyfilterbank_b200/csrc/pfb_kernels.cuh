@@ -50,6 +50,8 @@ struct SosParams {
     int Ktot, k0;         // sections per coefficient/state row, first section of this sweep
     int aligned;          // every row start is 16-byte aligned (selects the ALIGNED instantiation)
     int row0, nrows;      // scan kernel: coefficient rows covered by this launch
+    int dec;              // 1: keep only every second output sample (decimate by 2 on store), y rows hold n_out samples
+    int dec_phase;        // 0 / 1: parity of the kept input indices (output i <-> input 2 i + dec_phase)
 };
 
 // Coefficients of the rows one scan launch covers: c[(row - row0) * K + k][5].
@@ -286,6 +288,31 @@ struct CoopIO {
     }
 };
 
+// Decimating tile store: of tile elements [e0, e0 + TLEN) of every row keep those whose index within the
+// row has parity `phase`; element idx goes to output position (idx - phase) / 2 of the row at
+// ybase + row * out_stride.  Scalar streaming stores (the decimated stream is a small part of the traffic).
+template <typename T, typename LenFn>
+__device__ __forceinline__ void store_tile_dec(const char *buf, T *ybase, long long out_stride, long long e0, LenFn len,
+                                               int phase, int lane) {
+    using V = typename Vec16<T>::type;
+    constexpr int EPV = Vec16<T>::N;
+    const int rsub = lane >> 3, seg = lane & 7;
+    const long long e = e0 + seg * EPV;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = r * 4 + rsub;
+        const long long rl = len(row);
+        if (e < rl) {
+            const V v = *reinterpret_cast<const V *>(buf + row * kRowBytes + ((seg ^ (row & 7)) << 4));
+            const T *ev = reinterpret_cast<const T *>(&v);
+            T *prow = ybase + row * out_stride;
+#pragma unroll
+            for (int i = phase & 1; i < EPV; i += 2)
+                if (e + i < rl) st_stream1(prow + ((e + i - phase) >> 1), ev[i]);
+        }
+    }
+}
+
 // Per-lane tile load: the lane copies elements [e0, e0 + TLEN) of ITS row into its tile row (lanes
 // that share an input row hit the same global sectors, which the L1 coalesces).
 template <typename T, bool ALIGNED>
@@ -373,7 +400,8 @@ __global__ void __launch_bounds__(128, 4) sos_seq_kernel(const SosParams p) {
         cp_async_wait<1>();
         filter_row<T, A, K, EXACT, true>(myrow0 + cb * kTileBytes, key, c, w, TLEN);
         __syncwarp();
-        io.store_fast(buf0 + cb * kTileBytes, t * TLEN);
+        if (p.dec) store_tile_dec<T>(buf0 + cb * kTileBytes, ybase, p.ldy, t * TLEN, rowlen, p.dec_phase, lane);
+        else io.store_fast(buf0 + cb * kTileBytes, t * TLEN);
         __syncwarp();
     }
     for (long long t = tf; t < nt; ++t) {
@@ -385,7 +413,8 @@ __global__ void __launch_bounds__(128, 4) sos_seq_kernel(const SosParams p) {
         cp_async_wait<0>();
         filter_row<T, A, K, EXACT, true>(myrow0 + cb * kTileBytes, key, c, w, clamp_i(mylen - t * TLEN, TLEN));
         __syncwarp();
-        io.store(buf0 + cb * kTileBytes, t * TLEN, rowlen);
+        if (p.dec) store_tile_dec<T>(buf0 + cb * kTileBytes, ybase, p.ldy, t * TLEN, rowlen, p.dec_phase, lane);
+        else io.store(buf0 + cb * kTileBytes, t * TLEN, rowlen);
         __syncwarp();
     }
     if (active && n > 0) {
@@ -440,6 +469,8 @@ sos_scan_kernel(const __grid_constant__ SosParams p, const __grid_constant__ Coe
     const T *xbase = reinterpret_cast<const T *>(p.x);
     const T *xw = xbase + (long long)(q / p.xdiv) * p.ldx + (long long)j0 * L;   // warp's first chunk
     T *yw = reinterpret_cast<T *>(p.y) + (long long)q * p.ldy + (long long)j0 * L;
+    // decimating store: L is even, so chunk j starts at output index j * L / 2 and parities are chunk-local
+    T *yw_dec = reinterpret_cast<T *>(p.y) + (long long)q * p.ldy + (long long)j0 * (L >> 1);
     auto rowlen = [=](int row) -> long long {
         const long long r = n - (long long)(j0 + row) * L;
         return r <= 0 ? 0 : (r >= L ? L : r);
@@ -546,7 +577,8 @@ sos_scan_kernel(const __grid_constant__ SosParams p, const __grid_constant__ Coe
             __syncwarp();
             filter_row<T, A, K, false, true>(myrow0 + cb * kTileBytes, key, c, w, TLEN);
             __syncwarp();
-            io.store_fast(buf0 + cb * kTileBytes, t * TLEN);
+            if (p.dec) store_tile_dec<T>(buf0 + cb * kTileBytes, yw_dec, L >> 1, t * TLEN, rowlen, p.dec_phase, lane);
+            else io.store_fast(buf0 + cb * kTileBytes, t * TLEN);
             __syncwarp();
         }
         for (long long t = tf; t < nt; ++t) {   // bounds-checked tail, single-buffered
@@ -559,7 +591,8 @@ sos_scan_kernel(const __grid_constant__ SosParams p, const __grid_constant__ Coe
             __syncwarp();
             filter_row<T, A, K, false, true>(myrow0 + cb * kTileBytes, key, c, w, clamp_i(mylen - t * TLEN, TLEN));
             __syncwarp();
-            io.store(buf0 + cb * kTileBytes, t * TLEN, rowlen);
+            if (p.dec) store_tile_dec<T>(buf0 + cb * kTileBytes, yw_dec, L >> 1, t * TLEN, rowlen, p.dec_phase, lane);
+            else io.store(buf0 + cb * kTileBytes, t * TLEN, rowlen);
             __syncwarp();
         }
     }

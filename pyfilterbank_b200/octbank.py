@@ -9,6 +9,16 @@ libpfb_sos.so; `filterfun` names the arithmetic:
     'exact' -- sequential, separately rounded: bit-identical to sosfilt.c
 
 There is no CPU path ('py' / 'cprototype' of the reference are not provided).
+
+Decimating band path (`filter_decimated`, opt-in; the reference has no resampling anywhere): band b
+runs at fs / 2^m_b.  The semantics are composed from reference pieces so that a CPU oracle exists
+(SURVEY.md section 8 a6'):
+
+    stage 0 signal = the input; stage m signal = the stage m-1 signal filtered by
+    `butter_sos('lowpass', 8, 0.2)` (butterworth.py:16) with `sosfilter_double_c` arithmetic and
+    then decimated `[::2]`;
+    band b lives at the deepest stage m with  upper band edge * (1 + edge_correction) <= 0.2 * fs / 2^m
+    (m <= max_stage); its band-pass is `design_sosmat_band_passes` at the stage's rate (octbank.py:132).
 """
 import numpy as np
 import torch
@@ -114,6 +124,106 @@ class FractionalOctaveFilterbank:
             self.start_band, self.end_band, self.norm_freq, self.nth_oct)
         self._sosmat = design_sosmat_band_passes(self.order, self.band_edges, self.sample_rate,
                                                  self.edge_correction_percent)
+        self._dec_plan = None
+
+    # ------------------------------------------------------------------------------------------
+    # decimating band path (new, opt-in)
+    # ------------------------------------------------------------------------------------------
+    AA_ORDER = 8          # low-pass poles of the anti-alias filter of every halving stage (4 biquads)
+    AA_CUTOFF = 0.2       # its cutoff, normalised to the stage's INPUT rate
+    EDGE_LIMIT = 0.2      # a band may run at rate f if its (corrected) upper edge is <= EDGE_LIMIT * f
+    MAX_STAGE = 10
+
+    def decimation_plan(self):
+        """List of stages [{'m', 'rate', 'bands' (ascending band indices), 'sosmat' (6K, B_m)}],
+        stage 0 first; every band appears in exactly one stage.  Also sets `decimation_factors`."""
+        if self._dec_plan is not None:
+            return self._dec_plan
+        B = self.num_bands
+        fs = float(self.sample_rate)
+        hi = self.band_edges[1:] * (1 + self.edge_correction_percent * 1e-2)
+        m_b = np.zeros(B, dtype=int)
+        for b in range(B):
+            m = 0
+            while m < self.MAX_STAGE and hi[b] <= self.EDGE_LIMIT * fs / 2 ** (m + 1):
+                m += 1
+            m_b[b] = m
+        stages = []
+        for m in range(int(m_b.max()) + 1):
+            idx = np.nonzero(m_b == m)[0]
+            if len(idx) == 0:
+                stages.append({'m': m, 'rate': fs / 2 ** m, 'bands': [], 'sosmat': None})
+                continue
+            lo, hi_i = int(idx[0]), int(idx[-1])
+            assert len(idx) == hi_i - lo + 1           # contiguous because edges ascend
+            sosmat = design_sosmat_band_passes(self.order, self.band_edges[lo:hi_i + 2], fs / 2 ** m,
+                                               self.edge_correction_percent)
+            stages.append({'m': m, 'rate': fs / 2 ** m, 'bands': list(range(lo, hi_i + 1)),
+                           'sosmat': sosmat[:, :len(idx)]})
+        self._dec_plan = stages
+        self._dec_factors = 2 ** m_b
+        return stages
+
+    @property
+    def decimation_factors(self):
+        self.decimation_plan()
+        return self._dec_factors
+
+    @property
+    def aa_sos(self):
+        """(4, 6) anti-alias low-pass applied before every `[::2]`."""
+        return butter_sos('lowpass', self.AA_ORDER, self.AA_CUTOFF)
+
+    def filter_decimated(self, x, states=None):
+        """Per-band decimated analysis of x (N,) or (N, C) (numpy or CUDA tensor).
+
+        Returns (bands, states): `bands[b]` is band b at rate fs / decimation_factors[b], shape
+        (ceil-length N_b, C); `states` carries the anti-alias states, the decimator phases and the
+        band-pass states, so consecutive blocks of any length concatenate to the one-shot result.
+        No band signal is written at the full rate: the anti-alias stage stores every second sample
+        directly (PFB_DECIMATE2) and every stage's bands are filtered from the stage signal."""
+        plan = self.decimation_plan()
+        on_device = isinstance(x, torch.Tensor) and x.is_cuda
+        K = self.order
+        if on_device:
+            dev = x.device
+            sig = x.detach().to(torch.float64)
+            sig = sig.reshape(sig.shape[0], -1).t().contiguous()
+        else:
+            dev = _sf._device()
+            a = np.array(x, dtype=np.float64)
+            sig = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1).T)).to(dev)
+        C = sig.shape[0]
+        M = len(plan) - 1
+        aa = self.aa_sos
+        aa_bank = _sf.get_bank(aa.reshape(1, aa.shape[0], 6))
+        if states is None:
+            states = {'aa': [None] * M, 'phase': [0] * M, 'bands': [None] * len(plan)}
+        new = {'aa': [], 'phase': [], 'bands': []}
+        out = [None] * self.num_bands
+        mode = "seq" if self._exact else "auto"
+        for st in plan:
+            m = st['m']
+            if m > 0:
+                ph = int(states['phase'][m - 1])
+                n_in = sig.shape[1]
+                sig3, aa_st = _sf.bank_filter(aa_bank, sig, states['aa'][m - 1], mode=mode, exact=self._exact,
+                                              decimate=ph)
+                sig = sig3[:, 0, :]
+                new['aa'].append(aa_st)
+                new['phase'].append((ph + n_in) % 2)
+            if st['bands']:
+                Bm = len(st['bands'])
+                bank = _sf.get_bank(np.ascontiguousarray(st['sosmat'].T).reshape(Bm, K, 6))
+                y, bst = _sf.bank_filter(bank, sig if sig.is_contiguous() else sig.contiguous(),
+                                         states['bands'][m], mode=mode, exact=self._exact)
+                new['bands'].append(bst)
+                for j, b in enumerate(st['bands']):
+                    yb = y[:, j, :].t()                                   # (N_m, C) view
+                    out[b] = yb if on_device else yb.cpu().numpy()
+            else:
+                new['bands'].append(None)
+        return out, new
 
     def set_filterfun(self, filterfun_name):
         name = filterfun_name.lower()
@@ -128,10 +238,35 @@ class FractionalOctaveFilterbank:
         self.sosfilterfun = lambda x, sos, states=None: _sf.sosfilter_double_c(
             x, sos, states, mode=mode, exact=self._exact)
 
-    def filter_mimo_c(self, x, states=None):
-        """(N,) or (N, C) signal -> ((N, B, C) Fortran-ordered bands, flat states); octbank.py:412-434."""
-        return _sf.sosfilter_double_mimo_c(x, self.sosmat, states, mode="seq" if self._exact else "auto",
-                                           exact=self._exact)
+    def filter_mimo_c(self, x, states=None, weighting=None, weighting_states=None):
+        """(N,) or (N, C) signal -> ((N, B, C) Fortran-ordered bands, flat states); octbank.py:412-434.
+
+        weighting='A' | 'B' | 'C' (opt-in, not in the reference's signature) runs the SPL weighting
+        prefilter of splweighting.weight_signal (splweighting.py:61-80) on every channel on the device
+        before the bank, so the weighted signal never visits the host; the call then returns
+        (bands, states, weighting_states) and `weighting_states` ((C, ntaps-1) delay values in scipy's
+        zi convention) can be passed back for block-wise processing."""
+        if weighting is None:
+            return _sf.sosfilter_double_mimo_c(x, self.sosmat, states, mode="seq" if self._exact else "auto",
+                                               exact=self._exact)
+        from . import splweighting as _spl
+        b, a = _spl._weighting_coeff_design_funsd[weighting](self.sample_rate)
+        on_device = isinstance(x, torch.Tensor) and x.is_cuda
+        if on_device:
+            sig = x.detach().to(torch.float64)
+        else:
+            sig = torch.from_numpy(np.array(x, dtype=np.float64)).to(_sf._device())
+        n = sig.shape[0]
+        rows = sig.reshape(n, -1).t().contiguous()                          # (C, N)
+        if weighting_states is not None and not isinstance(weighting_states, torch.Tensor):
+            weighting_states = torch.from_numpy(np.array(weighting_states, dtype=np.float64)).to(rows.device)
+        w, wst = _spl.tf_filter(b, a, rows, None if weighting_states is None else weighting_states.clone())
+        y, st = _sf.sosfilter_double_mimo_c(w.t(), self.sosmat, states, mode="seq" if self._exact else "auto",
+                                            exact=self._exact)
+        if on_device:
+            return y, st, wst
+        return y.cpu().numpy() if isinstance(y, torch.Tensor) else y, \
+            st.cpu().numpy() if isinstance(st, torch.Tensor) else st, wst.cpu().numpy()
 
     def filter(self, x, ffilt=False, states=None):
         """Single-channel filtering, octbank.py:436-476: returns (y (N, B) float64, dict

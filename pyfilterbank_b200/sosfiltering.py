@@ -45,11 +45,12 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False, out=None):
+def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False, out=None, decimate=None):
     """Filter x (C, N) CUDA tensor (float32/float64, rows contiguous) through `bank`.
 
     Returns (y (C, B, N), states (C, B, K, 2)) CUDA tensors; `states` (if given) is updated in
-    place and returned.  This is the device-resident entry the wrappers below are built on."""
+    place and returned.  This is the device-resident entry the wrappers below are built on.
+    decimate=0/1: keep only the filtered samples 2 i + decimate (y is (C, B, (N - decimate + 1) // 2))."""
     if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("x must be a (C, N) CUDA tensor with contiguous rows")
     C, N = x.shape
@@ -64,12 +65,15 @@ def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False
         states = torch.zeros((C, B, K, 2), dtype=sdt, device=x.device)
     elif states.dtype != sdt or not states.is_contiguous() or states.numel() != C * B * K * 2:
         raise ValueError("states must be a contiguous %s tensor with C*B*K*2 elements" % sdt)
+    n_out = N if decimate is None else max(0, (N - int(decimate) + 1) // 2)
     if out is None:
-        out = torch.empty((C, B, N), dtype=x.dtype, device=x.device)
+        out = torch.empty((C, B, n_out), dtype=x.dtype, device=x.device)
     ldx = x.stride(0) if C > 1 else max(N, 1)
+    # a decimated block can be empty (one input sample on the odd phase): states still advance
+    dst = out if out.numel() else torch.empty(1, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        bank.filter_ptr(dtype, x.data_ptr(), ldx, out.data_ptr(), out.stride(1) if N > 0 else 1,
-                        states.data_ptr(), N, C, _lib.flags_of(mode, exact, arith64),
+        bank.filter_ptr(dtype, x.data_ptr(), ldx, dst.data_ptr(), max(out.stride(1), n_out, 1),
+                        states.data_ptr(), N, C, _lib.flags_of(mode, exact, arith64, decimate),
                         torch.cuda.current_stream().cuda_stream)
     return out, states
 

@@ -112,3 +112,92 @@ def test_weight_signal_golden(pfb):
     x2 = np.stack([g["x"], g["x"][::-1]])
     y2 = spl.weight_signal(x2, 48000, "A")
     assert rel_l2(y2[0], g["y_A_48000"]) <= TOL64
+
+
+# ---------------------------------------------------------------------------------------------
+# decimating band path (opt-in; composed semantics, see tests/golden/make_golden_composed.py)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", ["seq", "scan"])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_decimate2_store_equals_strided_full_output(pfb, mode, dt, monkeypatch):
+    """PFB_DECIMATE2: the kernel stores filtered samples 2 i + phase only; bit-identical to slicing the
+    full-rate output of the same kernel, for both phases, odd lengths, ragged channel counts."""
+    monkeypatch.setenv("PFB_NO_TMA", "1")     # the decimating store lives in the cp.async kernels
+    from pyfilterbank_b200.butterworth import butter_sos
+    rng = np.random.default_rng(5)
+    tdt = torch.float64 if dt == "f64" else torch.float32
+    sos = np.stack([butter_sos('lowpass', 8, 0.2), butter_sos('lowpass', 8, 0.1)])      # (2, 4, 6)
+    bank = pfb.Bank(sos)
+    for C, n in ((3, 40001), (37, 5000), (2, 17), (1, 1)):
+        x = torch.from_numpy(rng.standard_normal((C, n))).to("cuda", tdt)
+        yfull, sfull = pfb.bank_filter(bank, x, mode=mode)
+        for phase in (0, 1):
+            y, s = pfb.bank_filter(bank, x, mode=mode, decimate=phase)
+            assert y.shape == (C, 2, (n - phase + 1) // 2)
+            assert torch.equal(y, yfull[:, :, phase::2]), (C, n, phase)
+            assert torch.equal(s, sfull)
+
+
+def test_decimated_bank_golden(pfb):
+    g = golden("decimated_third_48k")
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000)
+    assert np.array_equal(np.log2(ofb.decimation_factors).astype(int), g["m_b"])
+    bands, st = ofb.filter_decimated(g["x"])
+    assert len(bands) == 33
+    for b in range(33):
+        ref = g["band_%02d" % b]
+        assert bands[b].shape == ref.shape, b
+        assert rel_l2(bands[b], ref) <= TOL64, (b, rel_l2(bands[b], ref))
+    # block-wise with an odd cut: decimator phases, anti-alias and band states are carried
+    cut = int(g["cut"])
+    ba, st = ofb.filter_decimated(g["x"][:cut])
+    bb, st = ofb.filter_decimated(g["x"][cut:], states=st)
+    for b in range(33):
+        ref = g["band_%02d" % b]
+        yy = np.concatenate([ba[b], bb[b]])
+        assert yy.shape == ref.shape, (b, yy.shape, ref.shape)
+        assert rel_l2(yy, ref) <= TOL64, b
+    # sequential, separately rounded kernels: bit-identical to the composition of the reference's functions
+    ofe = pfb.FractionalOctaveFilterbank(sample_rate=48000, filterfun='exact')
+    be, _ = ofe.filter_decimated(g["x"])
+    ba, st = ofe.filter_decimated(g["x"][:cut])
+    bb, st = ofe.filter_decimated(g["x"][cut:], states=st)
+    for b in range(33):
+        assert np.array_equal(be[b], g["band_%02d" % b]), b
+        assert np.array_equal(np.concatenate([ba[b], bb[b]]), g["band_%02d" % b]), b
+
+
+def test_decimated_bank_twelfth_octave_vs_oracle(pfb, oracle):
+    """cfg 3's bank (1/12 octave, order 6) on a short multi-channel signal, device-resident input."""
+    rng = np.random.default_rng(11)
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51)
+    x = rng.standard_normal((20000, 3))
+    ref = oracle.decimated_bank(x, ofb.decimation_plan(), ofb.aa_sos, 6)
+    bands, _ = ofb.filter_decimated(torch.from_numpy(x).cuda())
+    worst = 0.0
+    for b in range(ofb.num_bands):
+        yb = bands[b].cpu().numpy()
+        assert yb.shape == ref[b].shape
+        worst = max(worst, rel_l2(yb, ref[b]))
+    assert worst <= TOL64, worst
+
+
+def test_weighted_bank_golden(pfb):
+    g = golden("weighted_bank_48k")
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000)
+    for name in ("A", "C"):
+        y, st, wst = ofb.filter_mimo_c(g["x"], weighting=name)
+        ref = g["y_" + name]
+        assert y.shape == ref.shape
+        for b in range(33):
+            assert rel_l2(y[:, b], ref[:, b]) <= TOL64, (name, b, rel_l2(y[:, b], ref[:, b]))
+        # two blocks with carried bank and weighting states
+        ya, st, wst = ofb.filter_mimo_c(g["x"][:777], weighting=name)
+        yb, st, wst = ofb.filter_mimo_c(g["x"][777:], states=st, weighting=name, weighting_states=wst)
+        yy = np.concatenate([ya, yb])
+        for b in range(33):
+            assert rel_l2(yy[:, b], ref[:, b]) <= TOL64, (name, b)
+    ofe = pfb.FractionalOctaveFilterbank(sample_rate=48000, filterfun='exact')
+    y, st, _ = ofe.filter_mimo_c(g["x"], weighting="A")
+    assert np.array_equal(y, g["y_A"]) and np.array_equal(st, g["states_A"])
