@@ -11,7 +11,7 @@ libpfb_sos.so; `filterfun` names the arithmetic:
 There is no CPU path ('py' / 'cprototype' of the reference are not provided).
 
 Decimating band path (`filter_decimated`, opt-in; the reference has no resampling anywhere): band b
-runs at fs / 2^m_b.  The semantics are composed from reference pieces so that a CPU oracle exists
+runs at fs / 2^m_b.  The semantics are composed from reference pieces so that they can be checked
 (SURVEY.md section 8 a6'):
 
     stage 0 signal = the input; stage m signal = the stage m-1 signal filtered by
