@@ -53,6 +53,8 @@ struct Tables {          // device tables of one (arithmetic type, chunk length)
     double *gains = nullptr;  // [rows][K][2] = (G_k, 1/G_k) of the gain-normalised arithmetic, or null
     std::vector<int *> warm;  // per sweep: [rows] or null
     long long warm_total = 0;
+    double *H = nullptr;      // chunk-impulse-response tables of the GEMM-form pre-pass (pfb_tma.cuh), or null
+    long long *Hoff = nullptr;
 };
 
 int env_int(const char *name, int dflt) {
@@ -70,7 +72,7 @@ struct pfb_bank {
     std::vector<double> coef_host;        // [rows][K][5] = b0 b1 b2 a1 a2
     std::map<void *, std::pair<void *, size_t>> workspace;   // per stream: chunk-state scratch of the TMA path
     std::vector<Sweep> sweeps;
-    std::map<std::tuple<int, long long>, Tables> tables;
+    std::map<std::tuple<int, long long, int>, Tables> tables;
     std::mutex mu;
     pfb_launch_info last{};
     int sm_count = 148;
@@ -203,8 +205,31 @@ int ensure_coef(pfb_bank *b, int arith) {
     return PFB_OK;
 }
 
-int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
-    auto key = std::make_tuple(arith, L);
+// State impulse responses of one cascade: Hm[m * S + i] = state i (w1_0, w2_0, w1_1, ...) right after the
+// sample that follows a unit input sample by m samples (m = 0: the sample itself), in long double.
+void state_impulse_response(const double *sos_row, int Ks, long long W, std::vector<double> &Hm) {
+    const int S = 2 * Ks;
+    Hm.resize((size_t)W * S);
+    long double w[16][2] = {};
+    for (long long m = 0; m < W; ++m) {
+        long double x = m == 0 ? 1.0L : 0.0L;
+        for (int k = 0; k < Ks; ++k) {
+            const double *q = sos_row + 6 * k;
+            const long double w0 = x - (long double)q[4] * w[k][0] - (long double)q[5] * w[k][1];
+            x = (long double)q[0] * w0 + (long double)q[1] * w[k][0] + (long double)q[2] * w[k][1];
+            w[k][1] = w[k][0];
+            w[k][0] = w0;
+        }
+        for (int k = 0; k < Ks; ++k) {
+            Hm[(size_t)m * S + 2 * k] = (double)w[k][0];
+            Hm[(size_t)m * S + 2 * k + 1] = (double)w[k][1];
+        }
+    }
+}
+
+// tt: samples per tile step of the TMA kernels (0: tables for the cp.async scan kernel, no GEMM-form tables)
+int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **out) {
+    auto key = std::make_tuple(arith, L, tt);
     auto it = b->tables.find(key);
     if (it != b->tables.end()) {
         *out = &it->second;
@@ -216,6 +241,10 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
             cudaFree(kv.second.gains);
+        cudaFree(kv.second.H);
+        cudaFree(kv.second.Hoff);
+            cudaFree(kv.second.H);
+            cudaFree(kv.second.Hoff);
         }
         b->tables.clear();
     }
@@ -279,6 +308,43 @@ int ensure_tables(pfb_bank *b, int arith, long long L, const Tables **out) {
         if (ok) {
             PFB_CUDA(cudaMalloc((void **)&t.gains, g.size() * sizeof(double)));
             PFB_CUDA(cudaMemcpy(t.gains, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    // GEMM-form pre-pass tables (float64 arithmetic, shared bank, one sweep, at most 16 states)
+    if (arith == PFB_F64 && tt > 0 && b->sweeps.size() == 1 && !b->per_channel && 2 * b->K <= 16 &&
+        !env_int("PFB_NO_HFORM", 0)) {
+        const int S = 2 * b->K, MT = (S + 7) / 8;
+        const long long nt = L / tt;
+        std::vector<long long> off(b->rows);
+        std::vector<int> hwarm(b->rows);
+        PFB_CUDA(cudaMemcpy(hwarm.data(), t.warm[0], b->rows * sizeof(int), cudaMemcpyDeviceToHost));
+        long long total = 0;
+        for (int r = 0; r < b->rows; ++r) {
+            off[r] = total;
+            long long wt = ((long long)hwarm[r] + tt - 1) / tt;
+            if (wt > nt) wt = nt;
+            total += wt * tt * MT * 8;
+        }
+        if (total > 0 && total * 8 <= (256LL << 20)) {
+            std::vector<double> Hh((size_t)total, 0.0), Hm;
+            for (int r = 0; r < b->rows; ++r) {
+                long long wt = ((long long)hwarm[r] + tt - 1) / tt;
+                if (wt > nt) wt = nt;
+                const long long W = wt * tt;                       // window [L - W, L), sample t <-> lag m = L - 1 - t
+                state_impulse_response(&b->sos[(size_t)r * b->K * 6], b->K, W, Hm);
+                double *dst = &Hh[(size_t)off[r]];
+                for (long long tl = 0; tl < W; ++tl) {
+                    const long long m = W - 1 - tl;
+                    const long long step = tl >> 2;
+                    const int k = (int)(tl & 3);
+                    for (int i = 0; i < S; ++i)
+                        dst[(size_t)(step * MT + i / 8) * 32 + (i % 8) * 4 + k] = Hm[(size_t)m * S + i];
+                }
+            }
+            PFB_CUDA(cudaMalloc((void **)&t.H, (size_t)total * sizeof(double)));
+            PFB_CUDA(cudaMemcpy(t.H, Hh.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
+            PFB_CUDA(cudaMalloc((void **)&t.Hoff, b->rows * sizeof(long long)));
+            PFB_CUDA(cudaMemcpy(t.Hoff, off.data(), b->rows * sizeof(long long), cudaMemcpyHostToDevice));
         }
     }
     auto ins = b->tables.emplace(key, std::move(t));
@@ -394,6 +460,8 @@ void pfb_bank_destroy(pfb_bank *b) {
         for (void *p : kv.second.P) cudaFree(p);
         for (int *p : kv.second.warm) cudaFree(p);
         cudaFree(kv.second.gains);
+        cudaFree(kv.second.H);
+        cudaFree(kv.second.Hoff);
     }
     delete b;
 }
@@ -407,6 +475,10 @@ int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
             cudaFree(kv.second.gains);
+        cudaFree(kv.second.H);
+        cudaFree(kv.second.Hoff);
+            cudaFree(kv.second.H);
+            cudaFree(kv.second.Hoff);
         }
         b->tables.clear();
         b->warm_tol = tol;
@@ -534,7 +606,7 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
         const int J = 32 * groups;
         const long long Lt = n / J / tt * tt;
         if (Lt >= 4LL * tt && Lt < 0x7fffffffLL) {
-            rc = ensure_tables(b, arith, Lt, &tab);
+            rc = ensure_tables(b, arith, Lt, tt, &tab);
             if (rc) return rc;
             const long long n_main = Lt * J;
             CUtensorMap xmap, ymap;
@@ -603,10 +675,13 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
                     tp.warm = tab->warm[0];
                     tp.L = Lt;
                     tp.Q = Cg * b->B, tp.B = b->B, tp.C = Cg, tp.J = J, tp.nb = nb, tp.G = G;
-                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", nb), nb));
+                    // the GEMM-form pre-pass balances best with 4 bands per CTA (sweep in profiles/)
+                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", tab->H ? 4 : nb), nb));
                     tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
                     tp.Ktot = b->K, tp.k0 = 0;
                     tp.gains = tab->gains;
+                    tp.H = tab->H;
+                    tp.Hoff = tab->Hoff;
                     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, t_c0 = nullptr;
                     if (timed) {
                         for (cudaEvent_t &e : ev) e = b->tev_new();
@@ -674,7 +749,7 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
         const long long chunks = 32LL * warps;
         L = (n + chunks - 1) / chunks;
         L = std::max<long long>(tlen, (L + tlen - 1) / tlen * tlen);
-        rc = ensure_tables(b, arith, L, &tab);
+        rc = ensure_tables(b, arith, L, 0, &tab);
         if (rc) return rc;
     }
 

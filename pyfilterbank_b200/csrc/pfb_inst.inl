@@ -90,6 +90,14 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
     const int threads = (p.nb + 1) * 32;
     if (phases & 1) {
         if (ev) cudaEventRecord(ev[0], s);
+#if PFB_HAS_SCALED   // float64 arithmetic: GEMM-form pre-pass when the bank has its tables
+        if (p.H) {
+            auto kern_h = sos_hform_kernel<PFB_T, K, NBMAX>;
+            e = cudaFuncSetAttribute(kern_h, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+            if (e != cudaSuccess) return (int)e;
+            kern_h<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, xmap);
+        } else
+#endif
         kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap);
         if (ev) cudaEventRecord(ev[1], s);
         *launches += 1;

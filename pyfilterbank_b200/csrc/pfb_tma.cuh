@@ -43,6 +43,11 @@ struct TmaParams {
     // 20 FP64 operations per band sample for 4 sections; the product of the gains is applied once at
     // the output).  gains [B][K][2] = (G_k, 1 / G_k), G_k = b0_0 ... b0_{k-1}; null: plain arithmetic.
     const double *gains;
+    // Chunk-impulse-response (GEMM) form of the pre-pass, float64 arithmetic: z = H x over the pre-pass window.
+    // H: per band, per 4-sample step, MT tiles of 32 doubles in the m8n8k4 A-fragment order
+    // (lane l <-> state 8 mt + l / 4, sample l % 4); Hoff[b]: band b's offset in doubles; null: recurrence pre-pass.
+    const double *H;
+    const long long *Hoff;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -290,6 +295,159 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const A gk = SCALED ? (A)gain[2 * k] : A(1);
             zs[2 * k] = wst[k][0] * gk;
             zs[2 * k + 1] = wst[k][1] * gk;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Pre-pass in chunk-impulse-response form on the FP64 tensor-core path (DMMA m8n8k4).
+// The zero-state end state of a chunk is linear in its samples:  z[i] = sum_t Hrev[i][t] x[t]  with
+// Hrev[i][t] the response of state i at the chunk end to a unit sample at t (built on the host in long
+// double).  Per band warp that is a GEMM  Z[2K x 32 chunks] = Hrev[2K x W] X[W x 32 chunks]:
+// A fragments (Hrev, 8 states x 4 samples) stream from global memory / L2 and are shared by the four
+// n-tiles (8 chunks each) of the warp's 32 chunks, B fragments (x) come from the shared input tile.
+// 8 FMA-equivalents per chunk-sample instead of the recurrence's 14; DMMA and DFMA share one pipe on
+// B200 (profiles/r01_ubench_dmma_vs_dfma.txt), so the gain is the operation count, not concurrency.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename T, int K, int NBMAX>
+__global__ void __launch_bounds__((NBMAX + 1) * 32, NBMAX <= 7 ? 3 : 2)   // ~80 registers: accumulators + two A-fragment sets
+sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(1024) char smem[];
+    constexpr int TLEN = kRowBytes / (int)sizeof(T);
+    constexpr int TT = 2 * TLEN;
+    constexpr int S = 2 * K;
+    constexpr int MT = (S + 7) / 8;                          // 8-state tiles
+    constexpr int KS = TT / 4;                               // 4-sample steps per tile
+    constexpr unsigned kStageBytes = 2 * kTileBytes;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cta = blockIdx.x;
+    const int groups = p.J >> 5;
+    const int w = cta % groups;
+    const int cg = cta / groups;
+    const int nbw = p.nb_a, G = p.G_a;
+    const int g = cg % G, ch = cg / G;
+    const int b0 = g * nbw;
+    const int nb_here = min(nbw, p.B - b0);
+
+    char *xs = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kTmaStages * kStageBytes);
+    uint64_t *empty = full + kTmaStages;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nb_here);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long nt = p.L / TT;
+    int wmax = 0;
+    for (int i = 0; i < nb_here; ++i) wmax = max(wmax, p.warm[b0 + i]);
+    long long wt_max = ((long long)wmax + TT - 1) / TT;
+    if (wt_max > nt) wt_max = nt;
+    const long long t_first = nt - wt_max;
+
+    if (warp == nbw) {
+        if (lane == 0) {
+            for (long long t = t_first; t < nt; ++t) {
+                const long long it = t - t_first;
+                const int s = (int)(it % kTmaStages);
+                const unsigned ph = (unsigned)((it / kTmaStages) & 1);
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], kStageBytes);
+                char *dst = xs + s * kStageBytes;
+                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), 32 * w, ch);
+                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), 32 * w, ch);
+            }
+        }
+        return;
+    }
+    if (warp >= nb_here) return;
+
+    const int band = b0 + warp;
+    const int q = ch * p.B + band;
+    long long wt = ((long long)p.warm[band] + TT - 1) / TT;
+    if (wt > nt) wt = nt;
+    const long long t_mine = nt - wt;
+    // this lane's A elements: step ks of tile tl (counted from t_mine) -> Hb[((tl * KS + ks) * MT + mt) * 32 + lane]
+    const double *Hb = p.H + p.Hoff[band] + lane;
+    // this lane's B elements: row 8 n + lane / 4 (n-tile n), sample 4 ks + lane % 4 of the tile
+    const int key = lane >> 2;
+    const char *xlane = xs + key * kRowBytes;
+    double acc[MT][4][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[mt][n][0] = acc[mt][n][1] = 0.0;
+
+    long long t = t_first;
+    for (; t < t_mine; ++t) {            // tiles before this band's window are only released
+        const long long it = t - t_first;
+        const int s = (int)(it % kTmaStages);
+        mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    double a_cur[KS][MT];
+    if (t < nt) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) a_cur[ks][mt] = __ldg(Hb + (size_t)(ks * MT + mt) * 32);
+    }
+    for (; t < nt; ++t) {
+        const long long it = t - t_first;
+        const int s = (int)(it % kTmaStages);
+        // next tile's A fragments are requested before this tile's input is waited for
+        double a_nxt[KS][MT];
+        const bool more = t + 1 < nt;
+        const double *Hn = Hb + (size_t)(t + 1 - t_mine) * KS * MT * 32;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) a_nxt[ks][mt] = more ? __ldg(Hn + (size_t)(ks * MT + mt) * 32) : 0.0;
+        mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+        const char *xt = xlane + s * kStageBytes;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int smp = (4 * ks) % TLEN;                          // first sample of the step within its half tile
+            const char *xh = xt + ((4 * ks) / TLEN) * kTileBytes;
+            const int byte = (smp + (lane & 3)) * (int)sizeof(T);
+            const int off = (((byte >> 4) ^ key) << 4) + (byte & 15);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const double bv = (double)*reinterpret_cast<const T *>(xh + n * 8 * kRowBytes + off);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma884(acc[mt][n][0], acc[mt][n][1], a_cur[ks][mt], bv);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) a_cur[ks][mt] = a_nxt[ks][mt];
+    }
+    // C fragment: lane holds state 8 mt + lane / 4 of chunks 8 n + 2 (lane % 4) + {0, 1}
+    double *zs = reinterpret_cast<double *>(p.zs) + ((size_t)q * p.J + 32 * w) * S;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int i = 8 * mt + (lane >> 2);
+        if (i < S) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int c0 = 8 * n + 2 * (lane & 3);
+                zs[(size_t)c0 * S + i] = acc[mt][n][0];
+                zs[(size_t)(c0 + 1) * S + i] = acc[mt][n][1];
+            }
         }
     }
 }

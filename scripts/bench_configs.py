@@ -1,0 +1,110 @@
+"""Device-resident throughput of the other BASELINE.json configs (parity-test cases, not bench.py lines),
+on bounded blocks that fit one GPU.  One JSON line per case: band-samples/s (input-rate band-samples for
+the decimated mode), algorithmic bytes, fraction of the measured HBM peak.
+
+    python scripts/bench_configs.py [case ...]     cases: cfg1 cfg3_full cfg3_dec cfg4 cfg5 cfg5_f32
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pyfilterbank_b200 as p
+from pyfilterbank_b200 import gammatone as gt, splweighting as spl
+
+PEAK = 6551.0
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters=3, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, ms, units, alg_bytes, extra=None):
+    d = {"case": name, "ms": ms, "band_samples_per_s": units / (ms * 1e-3), "algorithmic_GB": alg_bytes / 1e9,
+         "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / PEAK}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def cfg1():
+    # default bank (fs 44100), 1 channel x 10 s, through the reference-facing call with numpy in/out
+    ofb = p.FractionalOctaveFilterbank()
+    x = np.random.default_rng(0).standard_normal(441000)
+    ofb.filter_mimo_c(x)
+    t0 = time.perf_counter(); its = 5
+    for _ in range(its):
+        y, st = ofb.filter_mimo_c(x)
+    dt = (time.perf_counter() - t0) / its
+    xt = torch.from_numpy(x).cuda().reshape(-1, 1)
+    ms = timeit(lambda: ofb.filter_mimo_c(xt))
+    report("cfg1 default bank 1 ch x 10 s f64 (numpy in/out, incl. H2D/D2H)", dt * 1e3, 441000 * 33, 441000 * 8 * 34,
+           {"device_resident_ms": ms, "device_resident_band_samples_per_s": 441000 * 33 / (ms * 1e-3)})
+
+
+def cfg3_full(C=1024, seconds=1):
+    ofb = p.FractionalOctaveFilterbank(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51)
+    B, K, n = ofb.num_bands, 6, 48000 * seconds
+    bank = p.Bank(np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6))
+    x = torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1
+    y = torch.empty(C, B, n, device="cuda", dtype=torch.float64)
+    ms = timeit(lambda: p.bank_filter(bank, x, None, out=y))
+    report("cfg3 1/12-oct order 6 full rate, %d ch x %d s f64" % (C, seconds), ms, C * B * n, C * n * 8 * (B + 1),
+           {"launch": bank.last_launch()})
+
+
+def cfg3_dec(C=1024, seconds=4):
+    ofb = p.FractionalOctaveFilterbank(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51)
+    n = 48000 * seconds
+    x = (torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1).t()          # (N, C) view
+    load = float((1.0 / ofb.decimation_factors).sum())
+    ms = timeit(lambda: ofb.filter_decimated(x), iters=2, warm=1)
+    alg = C * n * 8 * (1 + load)
+    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s f64" % (C, seconds), ms, C * ofb.num_bands * n, alg,
+           {"band_equivalents": load, "bands": ofb.num_bands})
+
+
+def cfg4(C=512, seconds=10):
+    gfb = gt.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
+    B, n = len(gfb.centerfrequencies), 16000 * seconds
+    x = torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1
+    ms = timeit(lambda: gt.fos_bank(x, gfb._coef_rows, 4), iters=2, warm=1)
+    report("cfg4 gammatone order 4, %d bands, %d signals x %d s @16 kHz, c128 out" % (B, C, seconds), ms, C * B * n,
+           C * n * (8 + 16 * B))
+
+
+def cfg5(C=1024, seconds=5, dtype=torch.float64):
+    ofb = p.FractionalOctaveFilterbank(sample_rate=48000)
+    B, K, n = 33, 4, 48000 * seconds
+    bank = p.Bank(np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6))
+    b, a = spl.a_weighting_coeffs_design(48000)
+    x = torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1
+    y = torch.empty(C, B, n, device="cuda", dtype=dtype)
+    esz = 8 if dtype == torch.float64 else 4
+
+    def run():
+        w, _ = spl.tf_filter(b, a, x)
+        p.bank_filter(bank, w if dtype == torch.float64 else w.to(dtype), None, out=y)
+    ms = timeit(run, iters=2, warm=1)
+    msw = timeit(lambda: spl.tf_filter(b, a, x), iters=2, warm=1)
+    report("cfg5 A-weighting + 1/3-oct bank, %d ch x %d s, %s" % (C, seconds, "f64" if esz == 8 else "f32 bank"), ms,
+           C * B * n, C * n * (8 + esz * B), {"weighting_kernel_ms": msw, "launch": bank.last_launch()})
+
+
+CASES = {"cfg1": cfg1, "cfg3_full": cfg3_full, "cfg3_dec": cfg3_dec, "cfg4": cfg4, "cfg5": cfg5,
+         "cfg5_f32": lambda: cfg5(dtype=torch.float32)}
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(CASES)):
+        CASES[name]()
+        torch.cuda.empty_cache()

@@ -215,13 +215,16 @@ def test_f32_bank_modes(pfb, oracle):
     assert np.array_equal(y3.cpu().numpy(), yf)
 
 
+@pytest.mark.parametrize("hform", [True, False])
 @pytest.mark.parametrize("scaled", [True, False])
-def test_tma_path_parity(pfb, oracle, scaled, monkeypatch):
+def test_tma_path_parity(pfb, oracle, scaled, hform, monkeypatch):
     """The TMA / mbarrier kernels (shared-input bank, 16-byte aligned rows, long signals): three
     launches (pre-pass, carry, output pass) + a ragged tail, plain and gain-normalised arithmetic,
-    carried states over two calls."""
+    recurrence and GEMM-form (DMMA) pre-pass, carried states over two calls."""
     if not scaled:
         monkeypatch.setenv("PFB_NO_SCALED", "1")
+    if not hform:
+        monkeypatch.setenv("PFB_NO_HFORM", "1")
     rng = np.random.default_rng(77)
     sos = _bank48()
     B, K = sos.shape[:2]
