@@ -76,15 +76,15 @@ struct pfb_bank {
     std::mutex mu;
     pfb_launch_info last{};
     int sm_count = 148;
+    std::vector<double> wproxy;   // per band: decay length used by the launch-shape cost model
     double warm_tol = 1e-11;   // relative L2 budget of the truncated pre-pass (0: always exact)
     // pfb_bank_timing_begin / _end: event pairs recorded around the kernels of the next `timing_left` calls
     struct TimeRec { cudaEvent_t a, b; int kind; };   // kind 0 pre-pass, 1 carry, 2 output pass, 3 whole call
     std::vector<TimeRec> trecs;
     std::vector<cudaEvent_t> tevents;
     int timing_left = 0, timing_calls = 0;
-    // channel-group pipeline of the TMA path: pre-pass kernels on s_lo, carry + output pass on s_hi
-    cudaStream_t s_lo = nullptr, s_hi = nullptr;
-    std::vector<cudaEvent_t> pipe_ev;
+    double *gains_dev[2] = {nullptr, nullptr};   // gain tables when no chunk tables are needed (single chunk)
+    double *gains_only(int arith);
 
     cudaEvent_t tev_new() {
         cudaEvent_t e = nullptr;
@@ -93,6 +93,33 @@ struct pfb_bank {
         return e;
     }
 };
+
+// Gain tables of the normalised float64 arithmetic (single-sweep banks with well-scaled b0 only):
+// [rows][K][2] = (G_k, 1 / G_k), G_k = b0_0 ... b0_{k-1}.  Null: plain arithmetic.
+double *pfb_bank::gains_only(int arith) {
+    if (arith != PFB_F64 || sweeps.size() != 1 || getenv("PFB_NO_SCALED")) return nullptr;
+    if (gains_dev[0]) return gains_dev[0];
+    if (gains_dev[1]) return nullptr;   // marker: this bank's gains are out of range
+    std::vector<double> g((size_t)rows * K * 2);
+    bool ok = true;
+    for (int r = 0; r < rows && ok; ++r) {
+        double G = 1.0;
+        for (int k = 0; k < K; ++k) {
+            g[((size_t)r * K + k) * 2] = G;
+            g[((size_t)r * K + k) * 2 + 1] = 1.0 / G;
+            G *= coef_host[((size_t)r * K + k) * 5];
+            const double m = std::fabs(G);
+            if (!(m > 1e-200 && m < 1e200)) ok = false;
+        }
+    }
+    if (!ok) {
+        cudaMalloc((void **)&gains_dev[1], 8);
+        return nullptr;
+    }
+    if (cudaMalloc((void **)&gains_dev[0], g.size() * sizeof(double)) != cudaSuccess) return nullptr;
+    cudaMemcpy(gains_dev[0], g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice);
+    return gains_dev[0];
+}
 
 namespace {
 
@@ -240,7 +267,6 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
         for (auto &kv : b->tables) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
-            cudaFree(kv.second.gains);
         cudaFree(kv.second.H);
         cudaFree(kv.second.Hoff);
             cudaFree(kv.second.H);
@@ -291,27 +317,9 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
         }
         t.P.push_back(d);
     }
-    // gain tables of the normalised float64 arithmetic (single-sweep banks with well-scaled b0 only)
-    if (arith == PFB_F64 && b->sweeps.size() == 1 && !env_int("PFB_NO_SCALED", 0)) {
-        std::vector<double> g((size_t)b->rows * b->K * 2);
-        bool ok = true;
-        for (int r = 0; r < b->rows && ok; ++r) {
-            double G = 1.0;
-            for (int k = 0; k < b->K; ++k) {
-                g[((size_t)r * b->K + k) * 2] = G;
-                g[((size_t)r * b->K + k) * 2 + 1] = 1.0 / G;
-                G *= b->coef_host[((size_t)r * b->K + k) * 5];
-                const double m = std::fabs(G);
-                if (!(m > 1e-200 && m < 1e200)) ok = false;
-            }
-        }
-        if (ok) {
-            PFB_CUDA(cudaMalloc((void **)&t.gains, g.size() * sizeof(double)));
-            PFB_CUDA(cudaMemcpy(t.gains, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
-        }
-    }
-    // GEMM-form pre-pass tables (float64 arithmetic, shared bank, one sweep, at most 16 states)
-    if (arith == PFB_F64 && tt > 0 && b->sweeps.size() == 1 && !b->per_channel && 2 * b->K <= 16 &&
+    t.gains = b->gains_only(arith);   // owned by the bank
+    // GEMM-form pre-pass tables (always float64; shared bank, one sweep, at most 16 states)
+    if (tt > 0 && b->sweeps.size() == 1 && !b->per_channel && 2 * b->K <= 16 &&
         !env_int("PFB_NO_HFORM", 0)) {
         const int S = 2 * b->K, MT = (S + 7) / 8;
         const long long nt = L / tt;
@@ -385,19 +393,35 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// rows x chunks x time view of a [rows][ld] signal cut into J chunks of L samples; box = 32 chunks x
-// one 128-byte half row, 128-byte swizzle (chunk c of row r at c ^ (r & 7), the layout filter_half reads)
-bool make_chunk_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long rows, long long ld) {
+// Chunked views of the signals for the TMA kernels.  A cascade's n_main = L * J samples are J chunks of L; a tile
+// holds JR chunks of CH channels.  Boxes are one 128-byte half row wide with the 128-byte swizzle (16-byte chunk c
+// of tile row r at c ^ (r & 7), the layout filter_half reads).
+//   x [C][ldx]      -> 3-D (time L, chunk J, channel C),          box (tlen, JR, CH)
+//   y [C][B][ldy]   -> 4-D (time L, chunk J, band B, channel C),  box (tlen, JR, 1, CH)
+bool make_x_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long C, long long ld, int JR, int CH) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t esz = dtype == PFB_F64 ? 8 : 4;
-    cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)J, (cuuint64_t)rows};
+    cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)J, (cuuint64_t)C};
     cuuint64_t strides[2] = {(cuuint64_t)L * esz, (cuuint64_t)ld * esz};
-    cuuint32_t box[3] = {(cuuint32_t)(pfb::kRowBytes / esz), 32, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(pfb::kRowBytes / esz), (cuuint32_t)JR, (cuuint32_t)CH};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, dtype == PFB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                      const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+bool make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int B, long long C, long long ld, int JR, int CH) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t esz = dtype == PFB_F64 ? 8 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)L, (cuuint64_t)J, (cuuint64_t)B, (cuuint64_t)C};
+    cuuint64_t strides[3] = {(cuuint64_t)L * esz, (cuuint64_t)ld * esz, (cuuint64_t)B * (cuuint64_t)ld * esz};
+    cuuint32_t box[4] = {(cuuint32_t)(pfb::kRowBytes / esz), (cuuint32_t)JR, 1, (cuuint32_t)CH};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, dtype == PFB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -453,13 +477,11 @@ void pfb_bank_destroy(pfb_bank *b) {
         if (b->coef[i]) cudaFree(b->coef[i]);
     for (auto &kv : b->workspace) cudaFree(kv.second.first);
     for (cudaEvent_t e : b->tevents) cudaEventDestroy(e);
-    for (cudaEvent_t e : b->pipe_ev) cudaEventDestroy(e);
-    if (b->s_lo) cudaStreamDestroy(b->s_lo);
-    if (b->s_hi) cudaStreamDestroy(b->s_hi);
+    cudaFree(b->gains_dev[0]);
+    cudaFree(b->gains_dev[1]);
     for (auto &kv : b->tables) {
         for (void *p : kv.second.P) cudaFree(p);
         for (int *p : kv.second.warm) cudaFree(p);
-        cudaFree(kv.second.gains);
         cudaFree(kv.second.H);
         cudaFree(kv.second.Hoff);
     }
@@ -474,7 +496,6 @@ int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
         for (auto &kv : b->tables) {
             for (void *p : kv.second.P) cudaFree(p);
             for (int *p : kv.second.warm) cudaFree(p);
-            cudaFree(kv.second.gains);
         cudaFree(kv.second.H);
         cudaFree(kv.second.Hoff);
             cudaFree(kv.second.H);
@@ -567,10 +588,20 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     const int arith = arith64 ? PFB_F64 : PFB_F32;
     const int Q = (int)Qll;
 
+    // TMA kernels (pfb_tma.cuh): shared-input banks, one sweep, 16-byte aligned rows.  They cover both regimes:
+    // few cascades (many time chunks per cascade) and many cascades (tile rows spread over channels, down to a
+    // single chunk per cascade = plain sequential filtering with warp-uniform coefficients and no pre-pass).
+    const int tt = 2 * tlen;
+    const bool tma_ok = !(flags & 0x100) && !dec && !exact && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
+                        !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 &&
+                        (ldy * esz) % 16 == 0 && n >= 4LL * tt &&
+                        b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections);
     if (mode == PFB_MODE_AUTO) {
         // enough independent cascades to fill the machine with one lane each -> no time split needed
         const long long lanes_to_fill = (long long)b->sm_count * 16 * 32;
-        mode = (exact || Qll >= lanes_to_fill / 2 || n < 4 * tlen) ? PFB_MODE_SEQ : PFB_MODE_SCAN;
+        if (exact || n < 4 * tlen) mode = PFB_MODE_SEQ;
+        else if (tma_ok) mode = PFB_MODE_SCAN;
+        else mode = Qll >= lanes_to_fill / 2 ? PFB_MODE_SEQ : PFB_MODE_SCAN;
     }
     int rc = PFB_OK;
     if (mode == PFB_MODE_SEQ) {
@@ -581,36 +612,55 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     int warps = 1;
     long long L = n;
     const Tables *tab = nullptr;
-    // TMA variant of the time-chunked path (pfb_tma.cuh): shared-input banks, one sweep, 16-byte aligned rows
-    if (mode == PFB_MODE_SCAN && !(flags & 0x100) && !dec && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
-        !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 && (ldy * esz) % 16 == 0 &&
-        b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections)) {
-        const int tt = 2 * tlen;
+    if (mode == PFB_MODE_SCAN && tma_ok) {
         int nbmax = env_int("PFB_TMA_NB", pfb::kTmaSmallBands);
         nbmax = std::max(1, std::min(nbmax, pfb::kTmaMaxBands));
         const int G0 = (b->B + nbmax - 1) / nbmax;
         const int nb = (b->B + G0 - 1) / G0;
         const int G = (b->B + nb - 1) / nb;
-        // chunk groups: fill whole waves of CTAs (2 resident per SM) while keeping chunks long
-        int groups = env_int("PFB_TMA_GROUPS", 0);
-        if (groups <= 0) {
-            double best = -1;
+        // Tile shape: J chunks per cascade, a tile's 32 rows = JR chunks x CH channels.  Candidates: J = 1, 2, .. 16
+        // (JR = J, CH = 32 / J) and J = 32 g (JR = 32, CH = 1).  Cost model: output pass / wave efficiency of its
+        // grid, plus the pre-pass share estimated from the bands' decay lengths.
+        int J = env_int("PFB_TMA_J", 0), JR = 0, CH = 0;
+        if (env_int("PFB_TMA_GROUPS", 0) > 0) J = 32 * env_int("PFB_TMA_GROUPS", 0);
+        if (J <= 0) {
+            if (b->wproxy.empty()) {   // decay length of every band (pre-pass window if chunks were unbounded)
+                b->wproxy.resize(b->B);
+                for (int r = 0; r < b->B; ++r)
+                    b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20,
+                                                       arith64 ? 1e-11 : 1e-8);
+            }
             const double slots = 2.0 * b->sm_count;
-            for (int g = 1; g <= 8; ++g) {
-                if (n / (32LL * g) < 64LL * tt && g > 1) break;
-                const double waves = (double)C * G * g / slots;
-                const double eff = waves / std::ceil(waves) - 0.01 * g;   // prefer longer chunks at equal fill
-                if (eff > best) best = eff, groups = g;
+            double best = 1e300;
+            for (int cand = 0; cand < 13; ++cand) {
+                const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
+                const int jr = std::min(j, 32), chn = 32 / jr;
+                if (n / j / tt * tt < (j > 1 ? 64LL : 4LL) * tt && j > 1) break;
+                const long long cb = (C + chn - 1) / chn;
+                const double ctas = (double)cb * G * (j / jr);
+                const double waves = ctas / slots;
+                double eff = waves >= 1 ? waves / std::ceil(waves) : waves;
+                eff *= (double)C / (double)(cb * chn);                         // ragged channel blocks idle lanes
+                double share = 0;
+                if (j > 1)
+                    for (int r = 0; r < b->B; ++r) share += std::min((double)j * b->wproxy[r], (double)n);
+                share /= (double)b->B * (double)n;
+                const double cost = (1.0 + 0.4 * share) / eff;
+                if (cost < best) best = cost, J = j;
             }
         }
-        const int J = 32 * groups;
+        JR = std::min(J, 32);
+        CH = 32 / JR;
+        if (JR * CH != 32 || J % JR != 0) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad chunk count %d", J);
+        const int groups = J / JR;
         const long long Lt = n / J / tt * tt;
         if (Lt >= 4LL * tt && Lt < 0x7fffffffLL) {
-            rc = ensure_tables(b, arith, Lt, tt, &tab);
-            if (rc) return rc;
+            if (J > 1) {
+                rc = ensure_tables(b, arith, Lt, tt, &tab);
+                if (rc) return rc;
+            }
             const long long n_main = Lt * J;
-            CUtensorMap xmap, ymap;
-            if (make_chunk_map(&xmap, dtype, x, Lt, J, C, ldx) && make_chunk_map(&ymap, dtype, y, Lt, J, Qll, ldy)) {
+            {
                 const size_t asz = arith64 ? 8 : 4;
                 // chunk-state scratch: kept per (bank, stream) so repeated calls do not allocate
                 const size_t need = (size_t)Q * J * 2 * b->K * asz;
@@ -627,102 +677,52 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
                 void *zs = ws.first;
                 const bool timed = b->timing_left > 0;
                 if (timed) { --b->timing_left; ++b->timing_calls; }
-                // Channel groups (experimental, PFB_TMA_CGROUPS > 1): the pre-pass of group g+1 (FP64-pipe bound,
-                // almost no DRAM traffic) runs on a low-priority stream beside the output pass of group g
-                // (DRAM bound) on a high-priority one.  Measured on cfg 2 (gpurun_out sweep, profiles/): no gain,
-                // the two kernels slow each other down by as much as they overlap, so the default is one group.
-                int NG = env_int("PFB_TMA_CGROUPS", 1);
-                NG = std::max(1, std::min(NG, std::min(C, 64)));
-                if (NG > 1 && !b->s_lo) {
-                    int lo = 0, hi = 0;
-                    PFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                    PFB_CUDA(cudaStreamCreateWithPriority(&b->s_lo, cudaStreamNonBlocking, lo));
-                    PFB_CUDA(cudaStreamCreateWithPriority(&b->s_hi, cudaStreamNonBlocking, hi));
-                }
-                while ((int)b->pipe_ev.size() < NG + 2) {
-                    cudaEvent_t e = nullptr;
-                    PFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                    b->pipe_ev.push_back(e);
-                }
-                cudaStream_t s_a = NG > 1 ? b->s_lo : stream, s_b = NG > 1 ? b->s_hi : stream;
-                cudaEvent_t t_fork = nullptr;
-                if (timed) {
-                    t_fork = b->tev_new();
-                    PFB_CUDA(cudaEventRecord(t_fork, stream));
-                }
-                if (NG > 1) {
-                    PFB_CUDA(cudaEventRecord(b->pipe_ev[NG], stream));
-                    PFB_CUDA(cudaStreamWaitEvent(s_a, b->pipe_ev[NG], 0));
-                    PFB_CUDA(cudaStreamWaitEvent(s_b, b->pipe_ev[NG], 0));
-                }
-                int launches = 0;
-                const double *ch = b->coef_host.data();
-                const size_t asz_state = (size_t)b->B * b->K * 2 * asz;
-                for (int g = 0; g < NG; ++g) {
-                    const int c0 = (int)((long long)C * g / NG), c1 = (int)((long long)C * (g + 1) / NG);
-                    const int Cg = c1 - c0;
-                    if (Cg <= 0) continue;
-                    const char *xg = (const char *)x + (size_t)c0 * ldx * esz;
-                    char *yg = (char *)y + (size_t)c0 * b->B * ldy * esz;
-                    CUtensorMap xmap, ymap;
-                    if (!make_chunk_map(&xmap, dtype, xg, Lt, J, Cg, ldx) ||
-                        !make_chunk_map(&ymap, dtype, yg, Lt, J, (long long)Cg * b->B, ldy))
-                        return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-                    pfb::TmaParams tp{};
-                    tp.zs = (char *)zs + (size_t)c0 * b->B * J * 2 * b->K * asz;
+                CUtensorMap xmap, ymap;
+                if (!make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH) ||
+                    !make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH))
+                    return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+                pfb::TmaParams tp{};
+                tp.zs = zs;
+                tp.states = states;
+                tp.L = Lt;
+                tp.Q = Q, tp.B = b->B, tp.C = C, tp.J = J, tp.nb = nb, tp.G = G;
+                tp.JR = JR, tp.CH = CH, tp.NW = J / JR, tp.CB = (C + CH - 1) / CH;
+                tp.Ktot = b->K, tp.k0 = 0;
+                tp.nb_a = nb;
+                if (tab) {
                     tp.P = tab->P[0];
-                    tp.states = (char *)states + (size_t)c0 * asz_state;
                     tp.warm = tab->warm[0];
-                    tp.L = Lt;
-                    tp.Q = Cg * b->B, tp.B = b->B, tp.C = Cg, tp.J = J, tp.nb = nb, tp.G = G;
-                    // the GEMM-form pre-pass balances best with 4 bands per CTA (sweep in profiles/)
-                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", tab->H ? 4 : nb), nb));
-                    tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
-                    tp.Ktot = b->K, tp.k0 = 0;
                     tp.gains = tab->gains;
                     tp.H = tab->H;
                     tp.Hoff = tab->Hoff;
-                    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, t_c0 = nullptr;
-                    if (timed) {
-                        for (cudaEvent_t &e : ev) e = b->tev_new();
-                        t_c0 = b->tev_new();
-                    }
-                    for (int phase = 1; phase <= 2; ++phase) {
-                        cudaStream_t sp = phase == 1 ? s_a : s_b;
-                        if (phase == 2) {
-                            if (NG > 1) {
-                                PFB_CUDA(cudaEventRecord(b->pipe_ev[g], s_a));
-                                PFB_CUDA(cudaStreamWaitEvent(s_b, b->pipe_ev[g], 0));
-                            }
-                            if (timed) PFB_CUDA(cudaEventRecord(t_c0, s_b));
-                        }
-                        int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase)
-                                  : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase)
-                                                  : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, sp, &launches, timed ? ev : nullptr, phase);
-                        if (err != 0)
-                            return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
-                    }
-                    if (timed) {
-                        b->trecs.push_back({ev[0], ev[1], 0});
-                        b->trecs.push_back({t_c0, ev[2], 1});
-                        b->trecs.push_back({ev[2], ev[3], 2});
-                    }
+                    // the GEMM-form pre-pass balances best with 4 bands per CTA (sweep in profiles/)
+                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", tab->H ? 4 : nb), nb));
+                } else {
+                    tp.gains = b->gains_only(arith);   // single chunk: no transition / pre-pass tables needed
                 }
-                if (NG > 1) {
-                    PFB_CUDA(cudaEventRecord(b->pipe_ev[NG + 1], s_b));
-                    PFB_CUDA(cudaStreamWaitEvent(stream, b->pipe_ev[NG + 1], 0));
-                }
+                tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
+                cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+                if (timed)
+                    for (cudaEvent_t &e : ev) e = b->tev_new();
+                int launches = 0;
+                const double *ch = b->coef_host.data();
+                int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
+                          : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
+                                          : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3);
+                if (err != 0)
+                    return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
                 if (timed) {
-                    cudaEvent_t t_join = b->tev_new();
-                    PFB_CUDA(cudaEventRecord(t_join, stream));
-                    b->trecs.push_back({t_fork, t_join, 3});
+                    b->trecs.push_back({ev[0], ev[1], 0});
+                    b->trecs.push_back({ev[1], ev[2], 1});
+                    b->trecs.push_back({ev[2], ev[3], 2});
+                    b->trecs.push_back({ev[0], ev[3], 3});
                 }
                 pfb_launch_info main_info{};
                 main_info.mode = PFB_MODE_SCAN;
                 main_info.kernels = launches;
                 main_info.warps_per_cascade = groups;
                 main_info.chunk = Lt;
-                main_info.warm_total = tab->warm_total * C;
+                main_info.warm_total = tab ? tab->warm_total * C : 0;
                 main_info.aligned = 2;   // 2 = TMA path
                 if (n_main < n) {        // the ragged end continues from the carried states
                     b->mu.unlock();

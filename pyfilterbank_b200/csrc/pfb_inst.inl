@@ -85,29 +85,34 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
     }
     constexpr int S = 2 * K;
     constexpr int LPC = S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16;
-    const unsigned grid = (unsigned)p.C * (unsigned)p.G * (unsigned)(p.J / 32);
-    const unsigned grid_a = (unsigned)p.C * (unsigned)p.G_a * (unsigned)(p.J / 32);
+    const unsigned grid = (unsigned)p.CB * (unsigned)p.G * (unsigned)p.NW;
+    const unsigned grid_a = (unsigned)p.CB * (unsigned)p.G_a * (unsigned)p.NW;
     const int threads = (p.nb + 1) * 32;
-    if (phases & 1) {
+    if ((phases & 1) && p.J == 1 && ev) {   // a single chunk per cascade needs no pre-pass
+        cudaEventRecord(ev[0], s);
+        cudaEventRecord(ev[1], s);
+    }
+    if ((phases & 1) && p.J > 1) {
         if (ev) cudaEventRecord(ev[0], s);
-#if PFB_HAS_SCALED   // float64 arithmetic: GEMM-form pre-pass when the bank has its tables
-        if (p.H) {
-            auto kern_h = sos_hform_kernel<PFB_T, K, NBMAX>;
+        if (p.H) {   // GEMM-form pre-pass (float64 DMMA for every arithmetic type) when the bank has its tables
+            auto kern_h = sos_hform_kernel<PFB_T, PFB_A, K, NBMAX>;
             e = cudaFuncSetAttribute(kern_h, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
             if (e != cudaSuccess) return (int)e;
             kern_h<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, xmap);
         } else
-#endif
-        kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap);
+            kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap);
         if (ev) cudaEventRecord(ev[1], s);
         *launches += 1;
     }
     if (phases & 2) {
-        sos_carry_kernel<PFB_A, K><<<(unsigned)(((long long)p.Q * LPC + 127) / 128), 128, 0, s>>>(p);
+        if (p.J > 1) {
+            sos_carry_kernel<PFB_A, K><<<(unsigned)(((long long)p.Q * LPC + 127) / 128), 128, 0, s>>>(p);
+            *launches += 1;
+        }
         if (ev) cudaEventRecord(ev[2], s);
         kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
         if (ev) cudaEventRecord(ev[3], s);
-        *launches += 2;
+        *launches += 1;
     }
     return (int)cudaGetLastError();
 }

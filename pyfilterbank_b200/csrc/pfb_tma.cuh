@@ -32,7 +32,10 @@ struct TmaParams {
     const int *warm;      // [B]
     long long L;          // chunk length, multiple of the tile time length
     int Q, B, C;
-    int J;                // chunks per cascade = 32 * groups
+    int J;                // chunks per cascade, a multiple of JR
+    int JR, CH;           // a tile's 32 rows are JR consecutive chunks of CH consecutive channels (JR * CH == 32):
+                          // many channels -> few (or one) chunks per cascade and (almost) no pre-pass
+    int NW, CB;           // chunk groups J / JR, channel blocks ceil(C / CH)
     int nb;               // band warps per CTA (output pass)
     int G;                // band groups = ceil(B / nb)
     int nb_a, G_a;        // the same for the pre-pass, whose CTAs are smaller: bands of one CTA should
@@ -84,6 +87,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
                  "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(map),
+                 "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
@@ -133,7 +141,8 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
     }
 }
 
-// cta = ((c * G) + g) * groups + w   (groups = J / 32), c counted from ch0
+// cta = ((cb * G) + g) * NW + w : channel block cb, band group g, chunk group w.
+// Tile row r <-> chunk JR * w + r % JR of channel CH * cb + r / JR.
 // PASS_B = false: pre-pass, writes zero-state chunk end states to zs; true: output pass from zs.
 template <typename T, typename A, int K, bool PASS_B, bool SCALED>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
@@ -147,11 +156,10 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     // indexed by it (the band's coefficients) can stay in uniform registers -- DFMA R, R, UR, R reads
     // two register pairs instead of three and issues at full FP64 rate
     const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
-    const int groups = p.J >> 5;
-    const int w = cta % groups;
-    const int cg = cta / groups;
+    const int w = cta % p.NW;
+    const int cg = cta / p.NW;
     const int nbw = PASS_B ? p.nb : p.nb_a, G = PASS_B ? p.G : p.G_a;
-    const int g = cg % G, ch = ch0 + cg / G;
+    const int g = cg % G, cb = ch0 + cg / G;
     const int b0 = g * nbw;
     const int nb_here = min(nbw, p.B - b0);
 
@@ -191,18 +199,20 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], kStageBytes);
                 char *dst = xs + s * kStageBytes;
-                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), 32 * w, ch);
-                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), 32 * w, ch);
+                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), p.JR * w, p.CH * cb);
+                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), p.JR * w, p.CH * cb);
             }
         }
         return;
     }
     if (warp >= nb_here) return;
 
-    // ---------------- consumers: one band per warp, one chunk per lane ----------------
+    // ---------------- consumers: one band per warp, one (channel, chunk) row per lane ----------------
     const int band = b0 + warp;
-    const int q = ch * p.B + band;
-    const int j = 32 * w + lane;
+    const int chn = p.CH * cb + lane / p.JR;
+    const bool row_ok = chn < p.C;                // channel blocks may be ragged: TMA clips the tile, lanes idle
+    const int q = (row_ok ? chn : 0) * p.B + band;
+    const int j = p.JR * w + lane % p.JR;
     A c[K][5], wst[K][2];
     // a second, independently reduced copy of the band index that is used for nothing but the
     // coefficient table, so its users stay on the uniform datapath
@@ -214,10 +224,12 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     A *zs = reinterpret_cast<A *>(p.zs) + ((size_t)q * p.J + j) * S;
     const double *gain = SCALED ? p.gains + (size_t)band * K * 2 : nullptr;
     if (PASS_B) {
+        // a single chunk per cascade starts from the carried-in states themselves (no pre-pass, no carry kernel)
+        const A *z0 = p.J == 1 ? reinterpret_cast<const A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2 : zs;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            wst[k][0] = zs[2 * k];
-            wst[k][1] = zs[2 * k + 1];
+            wst[k][0] = z0[2 * k];
+            wst[k][1] = z0[2 * k + 1];
             if (SCALED) { wst[k][0] *= (A)gain[2 * k + 1]; wst[k][1] *= (A)gain[2 * k + 1]; }
         }
     } else {
@@ -253,8 +265,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[s]);
-                tma_store_3d(&ymap, ybuf, (int)(t * TT), 32 * w, q);
-                tma_store_3d(&ymap, ybuf + kTileBytes, (int)(t * TT + TLEN), 32 * w, q);
+                tma_store_4d(&ymap, ybuf, (int)(t * TT), p.JR * w, band, p.CH * cb);
+                tma_store_4d(&ymap, ybuf + kTileBytes, (int)(t * TT + TLEN), p.JR * w, band, p.CH * cb);
                 bulk_commit();
             }
         }
@@ -280,7 +292,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     }
     if (PASS_B) {
         if (lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
-        if (j == p.J - 1) {              // the last chunk ends with the cascade's final state
+        if (row_ok && j == p.J - 1) {    // the last chunk ends with the cascade's final state
             A *st = reinterpret_cast<A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -289,7 +301,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 st[2 * k + 1] = wst[k][1] * gk;
             }
         }
-    } else {
+    } else if (row_ok) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const A gk = SCALED ? (A)gain[2 * k] : A(1);
@@ -315,7 +327,9 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <typename T, int K, int NBMAX>
+// T: signal type, Z: type of the chunk states (the arithmetic type of the other two kernels).  The GEMM itself
+// always runs in float64 -- for float32 banks that keeps the FP32 pipe free for the output pass.
+template <typename T, typename Z, int K, int NBMAX>
 __global__ void __launch_bounds__((NBMAX + 1) * 32, NBMAX <= 7 ? 3 : 2)   // ~80 registers: accumulators + two A-fragment sets
 sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(1024) char smem[];
@@ -328,11 +342,10 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int cta = blockIdx.x;
-    const int groups = p.J >> 5;
-    const int w = cta % groups;
-    const int cg = cta / groups;
+    const int w = cta % p.NW;
+    const int cg = cta / p.NW;
     const int nbw = p.nb_a, G = p.G_a;
-    const int g = cg % G, ch = cg / G;
+    const int g = cg % G, cb = cg / G;
     const int b0 = g * nbw;
     const int nb_here = min(nbw, p.B - b0);
 
@@ -365,8 +378,8 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], kStageBytes);
                 char *dst = xs + s * kStageBytes;
-                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), 32 * w, ch);
-                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), 32 * w, ch);
+                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), p.JR * w, p.CH * cb);
+                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), p.JR * w, p.CH * cb);
             }
         }
         return;
@@ -374,7 +387,6 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
     if (warp >= nb_here) return;
 
     const int band = b0 + warp;
-    const int q = ch * p.B + band;
     long long wt = ((long long)p.warm[band] + TT - 1) / TT;
     if (wt > nt) wt = nt;
     const long long t_mine = nt - wt;
@@ -436,17 +448,20 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) a_cur[ks][mt] = a_nxt[ks][mt];
     }
-    // C fragment: lane holds state 8 mt + lane / 4 of chunks 8 n + 2 (lane % 4) + {0, 1}
-    double *zs = reinterpret_cast<double *>(p.zs) + ((size_t)q * p.J + 32 * w) * S;
+    // C fragment: lane holds state 8 mt + lane / 4 of tile rows 8 n + 2 (lane % 4) + {0, 1}
+    Z *zs = reinterpret_cast<Z *>(p.zs);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int i = 8 * mt + (lane >> 2);
         if (i < S) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                const int c0 = 8 * n + 2 * (lane & 3);
-                zs[(size_t)c0 * S + i] = acc[mt][n][0];
-                zs[(size_t)(c0 + 1) * S + i] = acc[mt][n][1];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = 8 * n + 2 * (lane & 3) + e;
+                    const int chn = p.CH * cb + r / p.JR, j = p.JR * w + r % p.JR;
+                    if (chn < p.C) zs[(((size_t)chn * p.B + band) * p.J + j) * S + i] = (Z)acc[mt][n][e];
+                }
             }
         }
     }

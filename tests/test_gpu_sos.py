@@ -269,3 +269,32 @@ def test_tma_path_f32(pfb, oracle):
     for b in range(B):
         ref_err = rel_l2(yf[:, b], yd[:, b])
         assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (b, ref_err, rel_l2(y2[:, b], yd[:, b]))
+
+
+@pytest.mark.parametrize("J", [1, 2, 4, 8, 16, 32, 64])
+def test_tma_tile_shapes(pfb, oracle, J, monkeypatch):
+    """Tile rows of the TMA kernels are (channel, chunk) pairs: J chunks per cascade, 32 / min(J, 32)
+    channels per tile.  Every shape, ragged channel blocks included, matches the oracle; J = 1 is plain
+    sequential filtering with warp-uniform coefficients (no pre-pass, no carry kernel)."""
+    monkeypatch.setenv("PFB_TMA_J", str(J))
+    rng = np.random.default_rng(100 + J)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    bank = pfb.Bank(sos)
+    for C, n in ((1, 40000), (5, 33000 + 8), (37, 20480)):   # rows stay 16-byte aligned, lengths ragged
+        if n // J < 4 * 32:
+            continue
+        x = rng.standard_normal((C, n))
+        st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+        y0, s0 = oracle.sos_bank(x, sos, st0)
+        y1, s1 = pfb.bank_filter(bank, torch.from_numpy(x).cuda(), torch.from_numpy(st0.copy()).cuda())
+        info = bank.last_launch()
+        assert info["aligned"] == 2 and info["mode"] == 2, info
+        y1, s1 = y1.cpu().numpy(), s1.cpu().numpy()
+        worst = max(rel_l2(y1[:, b], y0[:, b]) for b in range(B))
+        assert worst <= TOL64, (C, n, worst)
+        assert rel_l2(s1, s0) <= 1e-8, (C, n)
+        xf = x.astype(np.float32)
+        yd, _ = oracle.sos_bank(xf.astype(np.float64), sos)
+        y2, _ = pfb.bank_filter(bank, torch.from_numpy(xf).cuda(), arith64=True)
+        assert max(rel_l2(y2.cpu().numpy()[:, b], yd[:, b]) for b in range(B)) <= 1e-6
