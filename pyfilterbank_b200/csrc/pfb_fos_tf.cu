@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(128, 3) fos_seq_kernel(const FosParams p) {
     }
 }
 
+constexpr int kTfStages = 4;
+
 struct TfParams {
     const double *x;
     double *y;
@@ -120,25 +122,39 @@ struct TfParams {
     double b[8], a[8];    // a[0] == 1 (normalised on the host like scipy does)
 };
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(128, 4) tf_seq_kernel(const __grid_constant__ TfParams p) {
+// One scipy _linear_filter step (direct form II transposed, a[0] == 1), every product and sum rounded separately
+// in scipy's order: the weighting filters have a 4-fold zero at z = 1, so FMA contraction alone moves the
+// result by ~1e-9 relative.   y = z0 + b0 x ; z[k] = (z[k+1] + x b[k+1]) - y a[k+1] ; z[NZ-1] = x b[NZ] - y a[NZ]
+template <int NZ>
+__device__ __forceinline__ double tf_step(double xi, const double (&b)[8], const double (&a)[8], double (&z)[NZ]) {
+    const double yi = __dadd_rn(z[0], __dmul_rn(b[0], xi));
+#pragma unroll
+    for (int k = 0; k < NZ - 1; ++k)
+        z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(xi, b[k + 1])), __dmul_rn(yi, a[k + 1]));
+    z[NZ - 1] = __dsub_rn(__dmul_rn(xi, b[NZ]), __dmul_rn(yi, a[NZ]));
+    return yi;
+}
+
+// One lane per row, one warp per CTA (the recurrence is latency bound: 3 dependent FP64 operations per sample,
+// so rows are spread over as many SM sub-partitions as possible).  NZ = taps - 1 delay values.
+template <int NZ, bool ALIGNED>
+__global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfParams p) {
     extern __shared__ __align__(128) char smem[];
-    constexpr int TLEN = 16, NZ = 7;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, key = lane & 7;
-    char *buf0 = smem + warp * 2 * kTileBytes;
-    const long long r0 = (long long)blockIdx.x * blockDim.x + warp * 32;
+    constexpr int TLEN = 16;
+    const int lane = threadIdx.x & 31, key = lane & 7;
+    char *buf0 = smem;
+    const long long r0 = (long long)blockIdx.x * 32;
     const long long r = r0 + lane;
     const int R = p.R;
     if (r0 >= R) return;
     const bool active = r < R;
     const long long n = p.n;
-    const int nz = p.ntaps - 1;
     double z[NZ];
 #pragma unroll
-    for (int k = 0; k < NZ; ++k) z[k] = (active && k < nz) ? p.z[(size_t)r * nz + k] : 0.0;
+    for (int k = 0; k < NZ; ++k) z[k] = active ? p.z[(size_t)r * NZ + k] : 0.0;
     double b[8], a[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { b[k] = k < p.ntaps ? p.b[k] : 0.0; a[k] = k < p.ntaps ? p.a[k] : 0.0; }
+    for (int k = 0; k < 8; ++k) { b[k] = p.b[k]; a[k] = p.a[k]; }
     const double *xrow = p.x + (active ? r : 0) * p.ldx;
     const long long mylen = active ? n : 0;
     CoopIO<double, ALIGNED> io(p.x, p.y + r0 * p.ldy, 0, p.ldy, lane);
@@ -146,43 +162,37 @@ __global__ void __launch_bounds__(128, 4) tf_seq_kernel(const __grid_constant__ 
     char *myrow = buf0 + lane * kRowBytes;
     const bool warp_full = r0 + 32 <= R;
     const long long nt = (n + TLEN - 1) / TLEN;
-    if (nt > 0) {
-        load_row_own<double, ALIGNED>(myrow, key, xrow, mylen, 0, p.x);
+    // kTfStages tiles in flight: one tile is only ~16 x 50 clocks of arithmetic, less than a DRAM round trip
+#pragma unroll
+    for (int t = 0; t < kTfStages - 1; ++t) {
+        if (t < nt) load_row_own<double, ALIGNED>(myrow + t * kTileBytes, key, xrow, mylen, (long long)t * TLEN, p.x);
         cp_async_commit();
     }
     for (long long t = 0; t < nt; ++t) {
-        const int cb = (int)(t & 1);
-        if (t + 1 < nt) {
-            load_row_own<double, ALIGNED>(myrow + (cb ^ 1) * kTileBytes, key, xrow, mylen, (t + 1) * TLEN, p.x);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        const int cb = (int)(t % kTfStages);
+        if (t + kTfStages - 1 < nt)
+            load_row_own<double, ALIGNED>(myrow + (int)((t + kTfStages - 1) % kTfStages) * kTileBytes, key, xrow, mylen,
+                                          (t + kTfStages - 1) * TLEN, p.x);
+        cp_async_commit();
+        cp_async_wait<kTfStages - 1>();
         const int valid = clamp_i(mylen - t * TLEN, TLEN);
         char *row = myrow + cb * kTileBytes;
+        if (valid == TLEN) {   // whole tile: registers in, registers out, no per-sample predicates
+            double2 v[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            double2 *slot = reinterpret_cast<double2 *>(row + ((v ^ key) << 4));
-            double2 io2 = *slot;
-            double *e = reinterpret_cast<double *>(&io2);
+            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const double2 *>(row + ((i ^ key) << 4));
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                if (2 * v + i < valid) {
-                    // scipy's _linear_filter: y = z0 + b0 x ; z[k] = z[k+1] + x b[k+1] - y a[k+1]
-                    // every product and sum rounded separately, in scipy's order: the weighting
-                    // filters have a 4-fold zero at z = 1, so FMA contraction alone moves the result
-                    // by ~1e-9 relative
-                    const double xi = e[i];
-                    const double yi = nz > 0 ? __dadd_rn(z[0], __dmul_rn(b[0], xi)) : __dmul_rn(b[0], xi);
-#pragma unroll
-                    for (int k = 0; k < NZ - 1; ++k)
-                        z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(xi, b[k + 1])), __dmul_rn(yi, a[k + 1]));
-                    z[NZ - 1] = __dsub_rn(__dmul_rn(xi, b[NZ]), __dmul_rn(yi, a[NZ]));
-                    e[i] = yi;
-                }
+            for (int i = 0; i < 8; ++i) {
+                v[i].x = tf_step<NZ>(v[i].x, b, a, z);
+                v[i].y = tf_step<NZ>(v[i].y, b, a, z);
             }
-            *slot = io2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<double2 *>(row + ((i ^ key) << 4)) = v[i];
+        } else {
+            for (int i = 0; i < valid; ++i) {
+                double *e = reinterpret_cast<double *>(row + (((i >> 1) ^ key) << 4) + (i & 1) * 8);
+                *e = tf_step<NZ>(*e, b, a, z);
+            }
         }
         __syncwarp();
         if ((t + 1) * TLEN <= n && warp_full) io.store_fast(buf0 + cb * kTileBytes, t * TLEN);
@@ -191,8 +201,7 @@ __global__ void __launch_bounds__(128, 4) tf_seq_kernel(const __grid_constant__ 
     }
     if (active && n > 0) {
 #pragma unroll
-        for (int k = 0; k < NZ; ++k)
-            if (k < nz) p.z[(size_t)r * nz + k] = z[k];
+        for (int k = 0; k < NZ; ++k) p.z[(size_t)r * NZ + k] = z[k];
     }
 }
 
@@ -226,12 +235,27 @@ int launch_fos(const FosParams &p, int order, bool aligned, cudaStream_t s) {
     }
 }
 
-int launch_tf(const TfParams &p, bool aligned, cudaStream_t s) {
-    const int warps = 4, smem = warps * 2 * kTileBytes;
-    const unsigned grid = (unsigned)((p.R + warps * 32 - 1) / (warps * 32));
-    if (aligned) tf_seq_kernel<true><<<grid, warps * 32, smem, s>>>(p);
-    else tf_seq_kernel<false><<<grid, warps * 32, smem, s>>>(p);
+template <int NZ>
+static int run_tf(const TfParams &p, bool aligned, cudaStream_t s) {
+    const int smem = kTfStages * kTileBytes;
+    const unsigned grid = (unsigned)((p.R + 31) / 32);
+    if (aligned) tf_seq_kernel<NZ, true><<<grid, 32, smem, s>>>(p);
+    else tf_seq_kernel<NZ, false><<<grid, 32, smem, s>>>(p);
     return (int)cudaGetLastError();
+}
+
+int launch_tf(const TfParams &p, bool aligned, cudaStream_t s) {
+    switch (p.ntaps - 1) {
+        case 0:   // pure gain: one (always zero) delay value keeps the state layout [R][max(taps - 1, 1)]
+        case 1: return run_tf<1>(p, aligned, s);
+        case 2: return run_tf<2>(p, aligned, s);
+        case 3: return run_tf<3>(p, aligned, s);
+        case 4: return run_tf<4>(p, aligned, s);
+        case 5: return run_tf<5>(p, aligned, s);
+        case 6: return run_tf<6>(p, aligned, s);
+        case 7: return run_tf<7>(p, aligned, s);
+        default: return (int)cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace pfb
