@@ -11,6 +11,8 @@
 //
 // One lane per cascade / row, sequential in time, through the same swizzled row-tile engine as the
 // SOS kernels (pfb_kernels.cuh).
+#include <cstdlib>
+
 #include "pfb_kernels.cuh"
 #include "../../include/pfb_sos.h"
 
@@ -111,8 +113,6 @@ __global__ void __launch_bounds__(128, 3) fos_seq_kernel(const FosParams p) {
     }
 }
 
-constexpr int kTfStages = 4;
-
 struct TfParams {
     const double *x;
     double *y;
@@ -137,7 +137,7 @@ __device__ __forceinline__ double tf_step(double xi, const double (&b)[8], const
 
 // One lane per row, one warp per CTA (the recurrence is latency bound: 3 dependent FP64 operations per sample,
 // so rows are spread over as many SM sub-partitions as possible).  NZ = taps - 1 delay values.
-template <int NZ, bool ALIGNED>
+template <int NZ, bool ALIGNED, int kTfStages>
 __global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfParams p) {
     extern __shared__ __align__(128) char smem[];
     constexpr int TLEN = 16;
@@ -237,10 +237,13 @@ int launch_fos(const FosParams &p, int order, bool aligned, cudaStream_t s) {
 
 template <int NZ>
 static int run_tf(const TfParams &p, bool aligned, cudaStream_t s) {
-    const int smem = kTfStages * kTileBytes;
     const unsigned grid = (unsigned)((p.R + 31) / 32);
-    if (aligned) tf_seq_kernel<NZ, true><<<grid, 32, smem, s>>>(p);
-    else tf_seq_kernel<NZ, false><<<grid, 32, smem, s>>>(p);
+    const char *v = getenv("PFB_TF_STAGES");
+    const int st = v ? atoi(v) : 2;
+    if (!aligned) tf_seq_kernel<NZ, false, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
+    else if (st == 4) tf_seq_kernel<NZ, true, 4><<<grid, 32, 4 * kTileBytes, s>>>(p);
+    else if (st == 3) tf_seq_kernel<NZ, true, 3><<<grid, 32, 3 * kTileBytes, s>>>(p);
+    else tf_seq_kernel<NZ, true, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -298,3 +298,28 @@ def test_tma_tile_shapes(pfb, oracle, J, monkeypatch):
         yd, _ = oracle.sos_bank(xf.astype(np.float64), sos)
         y2, _ = pfb.bank_filter(bank, torch.from_numpy(xf).cuda(), arith64=True)
         assert max(rel_l2(y2.cpu().numpy()[:, b], yd[:, b]) for b in range(B)) <= 1e-6
+
+
+@pytest.mark.parametrize("block_mb", [2048, 1, 0])
+def test_bank_filter_host_streaming(pfb, oracle, block_mb, monkeypatch):
+    """pfb_bank_filter_host on numpy buffers: whole-signal channel groups (one or several channels per group)
+    and, when a channel's band signals exceed the device block, time blocks with carried states."""
+    from pyfilterbank_b200 import _lib
+    monkeypatch.setenv("PFB_HOST_BLOCK_MB", str(block_mb))
+    rng = np.random.default_rng(31)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    C, n = 5, 24000 + 8
+    x = rng.standard_normal((C, n))
+    st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+    y0, s0 = oracle.sos_bank(x, sos, st0)
+    bank = pfb.Bank(sos)
+    y = np.empty((C, B, n))
+    st = st0.copy()
+    bank.filter_host(_lib.PFB_F64, x, n, y, n, st, n, C)
+    assert max(rel_l2(y[:, b], y0[:, b]) for b in range(B)) <= TOL64
+    assert rel_l2(st, s0) <= 1e-8
+    st = st0.copy()
+    ye = np.empty((C, B, n))
+    bank.filter_host(_lib.PFB_F64, x, n, ye, n, st, n, C, _lib.flags_of("seq", exact=True))
+    assert np.array_equal(ye, y0) and np.array_equal(st, s0)
