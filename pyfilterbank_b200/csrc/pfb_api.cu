@@ -396,12 +396,14 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
+}  // namespace
+
 // Chunked views of the signals for the TMA kernels.  A cascade's n_main = L * J samples are J chunks of L; a tile
 // holds JR chunks of CH channels.  Boxes are one 128-byte half row wide with the 128-byte swizzle (16-byte chunk c
 // of tile row r at c ^ (r & 7), the layout filter_half reads).
 //   x [C][ldx]      -> 3-D (time L, chunk J, channel C),          box (tlen, JR, CH)
 //   y [C][B][ldy]   -> 4-D (time L, chunk J, band B, channel C),  box (tlen, JR, 1, CH)
-bool make_x_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long C, long long ld, int JR, int CH) {
+bool pfb::make_x_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long C, long long ld, int JR, int CH) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t esz = dtype == PFB_F64 ? 8 : 4;
@@ -414,7 +416,7 @@ bool make_x_map(CUtensorMap *map, int dtype, const void *base, long long L, int 
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
-bool make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int B, long long C, long long ld, int JR, int CH) {
+bool pfb::make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int B, long long C, long long ld, int JR, int CH) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t esz = dtype == PFB_F64 ? 8 : 4;
@@ -427,8 +429,6 @@ bool make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
-
-}  // namespace
 
 int pfb_set_error(int status, const char *msg) {   // used by the other translation units
     g_status = status;
@@ -685,8 +685,8 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
                 const bool timed = b->timing_left > 0;
                 if (timed) { --b->timing_left; ++b->timing_calls; }
                 CUtensorMap xmap, ymap;
-                if (!make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH) ||
-                    !make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH))
+                if (!pfb::make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH) ||
+                    !pfb::make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH))
                     return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
                 pfb::TmaParams tp{};
                 tp.zs = zs;

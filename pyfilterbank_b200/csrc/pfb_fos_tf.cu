@@ -13,7 +13,12 @@
 // SOS kernels (pfb_kernels.cuh).
 #include <cstdlib>
 
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "pfb_kernels.cuh"
+#include "pfb_fos_tma.cuh"
 #include "../../include/pfb_sos.h"
 
 namespace pfb {
@@ -261,6 +266,187 @@ int launch_tf(const TfParams &p, bool aligned, cudaStream_t s) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA path of the gammatone bank: launch planning and per-call tables (cheap: 2*order x 2*order matrices).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// one sample of the cascade on long double states (re, im per stage), returns nothing (states only)
+void fos_step_ld(const double *c3, int order, long double *z, long double x) {
+    const long double g = c3[0], cr = c3[1], ci = c3[2];
+    long double yr = z[0] + g * x, yi = z[1];
+    z[0] = cr * yr - ci * yi;
+    z[1] = cr * yi + ci * yr;
+    for (int s = 1; s < order; ++s) {
+        yr = z[2 * s] + yr;
+        yi = z[2 * s + 1] + yi;
+        z[2 * s] = cr * yr - ci * yi;
+        z[2 * s + 1] = cr * yi + ci * yr;
+    }
+}
+
+// P = M^L of the zero-input state map, rounded to double
+void fos_transition(const double *c3, int order, long long L, double *P) {
+    const int S = 2 * order;
+    std::vector<long double> M(S * S), R(S * S, 0.0L), T(S * S);
+    for (int jc = 0; jc < S; ++jc) {
+        long double z[16] = {};
+        z[jc] = 1.0L;
+        fos_step_ld(c3, order, z, 0.0L);
+        for (int i = 0; i < S; ++i) M[i * S + jc] = z[i];
+    }
+    for (int i = 0; i < S; ++i) R[i * S + i] = 1.0L;
+    auto matmul = [&](const std::vector<long double> &a, const std::vector<long double> &b, std::vector<long double> &c) {
+        for (int i = 0; i < S; ++i)
+            for (int jc = 0; jc < S; ++jc) {
+                long double acc = 0;
+                for (int k = 0; k < S; ++k) acc += a[i * S + k] * b[k * S + jc];
+                c[i * S + jc] = acc;
+            }
+    };
+    for (long long e = L; e > 0; e >>= 1) {
+        if (e & 1) { matmul(R, M, T); R = T; }
+        if (e > 1) { matmul(M, M, T); M = T; }
+    }
+    for (int i = 0; i < S * S; ++i) P[i] = (double)R[i];
+}
+
+// decay window: smallest W (multiple of 16) such that the state response to a unit sample W samples back is
+// below tol relative to its peak (the poles all have |c| < 1; order repeated poles decay like t^(order-1) |c|^t)
+long long fos_warm(const double *c3, int order, long long L, double tol) {
+    long double z[16] = {};
+    fos_step_ld(c3, order, z, 1.0L);
+    long double peak = 0;
+    for (long long m = 1; m < L; ++m) {
+        long double e = 0;
+        for (int i = 0; i < 2 * order; ++i) e += z[i] * z[i];
+        if (e > peak) peak = e;
+        if (e <= (long double)tol * tol * peak && m > 8 * order) return std::min<long long>(L, (m + 15) / 16 * 16);
+        fos_step_ld(c3, order, z, 0.0L);
+    }
+    return L;
+}
+
+}  // namespace
+
+template <int ORDER>
+static int run_fos_tma(const FosTmaParams &p, const FosCoef &tab, const TmaParams &cp, const CUtensorMap &xmap,
+                       const CUtensorMap &ymap, cudaStream_t s) {
+    auto ka = fos_tma_kernel<ORDER, false>;
+    auto kb = fos_tma_kernel<ORDER, true>;
+    const int smem_a = kFosStages * kTileBytes + 2 * kFosStages * 8;
+    const int smem_b = (kFosStages + 2 * p.nb) * kTileBytes + 2 * kFosStages * 8;
+    cudaError_t e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned grid = (unsigned)p.CB * (unsigned)p.G * (unsigned)p.NW;
+    const int threads = (p.nb + 1) * 32;
+    if (p.J > 1) {
+        ka<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap);
+        constexpr int S = 2 * ORDER;
+        constexpr int LPC = S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16;
+        sos_carry_kernel<double, ORDER><<<(unsigned)(((long long)p.Q * LPC + 127) / 128), 128, 0, s>>>(cp);
+    }
+    kb<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+    return (int)cudaGetLastError();
+}
+
+// returns 0 on success, a cudaError_t otherwise; *n_done = samples filtered (0 when the shapes do not fit this
+// path; a ragged end [n_done, n) is left to the caller, states carried)
+int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, const double *coef_host, int B, int order,
+                   double *states, long long n, int C, cudaStream_t s, long long *n_done) {
+    *n_done = 0;
+    const int S = 2 * order;
+    if (B > (int)(kCoefBytes / 24) || n < 64 || getenv("PFB_NO_TMA")) return 0;
+    int sm_count = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const int G0 = (B + kFosMaxBands - 1) / kFosMaxBands;
+    const int nb = (B + G0 - 1) / G0, G = (B + nb - 1) / nb;
+    // chunks per signal: fill the machine (2 CTAs per SM), prefer few chunks (the pre-pass is cheap: decay windows
+    // of gammatone filters are a few thousand samples)
+    std::vector<long long> wproxy(B);
+    for (int b = 0; b < B; ++b) wproxy[b] = fos_warm(coef_host + 3 * b, order, 1 << 20, 1e-13);
+    int J = 0;
+    if (const char *v = getenv("PFB_FOS_J")) J = atoi(v);
+    if (J <= 0) {
+        const double slots = 2.0 * sm_count;
+        double best = 1e300;
+        for (int cand = 0; cand < 13; ++cand) {
+            const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
+            const int jr = std::min(j, 32), chn = 32 / jr;
+            if (j > 1 && n / j / 16 * 16 < 64 * 16) break;
+            const long long cb = (C + chn - 1) / chn;
+            const double waves = (double)cb * G * (j / jr) / slots;
+            double eff = waves >= 1 ? waves / std::ceil(waves) : waves;
+            eff *= (double)C / (double)(cb * chn);
+            double share = 0;
+            if (j > 1)
+                for (int b = 0; b < B; ++b) share += std::min((double)j * (double)wproxy[b], (double)n);
+            share /= (double)B * (double)n;
+            const double cost = (1.0 + 0.7 * share) / eff;
+            if (cost < best) best = cost, J = j;
+        }
+    }
+    const int JR = std::min(J, 32), CH = 32 / JR;
+    if (JR * CH != 32 || J % JR) return (int)cudaErrorInvalidValue;
+    const long long Lt = n / J / 16 * 16;
+    if (Lt < 64 || 2 * Lt >= 0x7fffffffLL) return 0;
+    const long long n_main = Lt * J, Q = (long long)C * B;
+    CUtensorMap xmap, ymap;
+    if (!make_x_map(&xmap, PFB_F64, x, Lt, J, C, ldx, JR, CH) ||
+        !make_y_map(&ymap, PFB_F64, y, 2 * Lt, J, B, C, 2 * ldy, JR, CH))
+        return 0;
+    static thread_local FosCoef tab;
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < 3; ++i) tab.c[b][i] = coef_host[3 * b + i];
+    FosTmaParams p{};
+    p.states = states;
+    p.L = Lt;
+    p.Q = (int)Q, p.B = B, p.C = C, p.J = J, p.JR = JR, p.CH = CH, p.NW = J / JR, p.CB = (C + CH - 1) / CH;
+    p.nb = nb, p.G = G;
+    TmaParams cp{};
+    void *scratch = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (J > 1) {
+        std::vector<double> P((size_t)B * S * S);
+        std::vector<int> warm(B);
+        for (int b = 0; b < B; ++b) {
+            fos_transition(coef_host + 3 * b, order, Lt, &P[(size_t)b * S * S]);
+            warm[b] = (int)std::min<long long>(fos_warm(coef_host + 3 * b, order, Lt, 1e-13), Lt);
+        }
+        const size_t zs_bytes = (size_t)Q * J * S * 8, P_bytes = P.size() * 8, w_bytes = (size_t)B * 4;
+        const size_t offP = (zs_bytes + 255) / 256 * 256, offW = offP + (P_bytes + 255) / 256 * 256;
+        e = cudaMallocAsync(&scratch, offW + w_bytes, s);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync((char *)scratch + offP, P.data(), P_bytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)scratch + offW, warm.data(), w_bytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // P / warm are host temporaries
+        if (e != cudaSuccess) return (int)e;
+        p.zs = scratch;
+        p.warm = (const int *)((char *)scratch + offW);
+        cp.zs = scratch;
+        cp.P = (char *)scratch + offP;
+        cp.states = states;
+        cp.Q = (int)Q, cp.B = B, cp.J = J, cp.Ktot = order, cp.k0 = 0;
+    }
+    int err;
+    switch (order) {
+        case 1: err = run_fos_tma<1>(p, tab, cp, xmap, ymap, s); break;
+        case 2: err = run_fos_tma<2>(p, tab, cp, xmap, ymap, s); break;
+        case 3: err = run_fos_tma<3>(p, tab, cp, xmap, ymap, s); break;
+        case 4: err = run_fos_tma<4>(p, tab, cp, xmap, ymap, s); break;
+        case 5: err = run_fos_tma<5>(p, tab, cp, xmap, ymap, s); break;
+        case 6: err = run_fos_tma<6>(p, tab, cp, xmap, ymap, s); break;
+        case 8: err = run_fos_tma<8>(p, tab, cp, xmap, ymap, s); break;
+        default: err = (int)cudaErrorInvalidValue;
+    }
+    if (scratch) cudaFreeAsync(scratch, s);
+    if (err) return err;
+    *n_done = n_main;
+    return 0;
+}
+
 }  // namespace pfb
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +465,16 @@ int pfb_fos_bank_c128(const double *x, int64_t ldx, double *y, int64_t ldy, cons
         return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: order must be 1..6 or 8");
     if ((long long)C * B > 0x7fffffffLL) return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: C*B too large");
     cudaStream_t s = (cudaStream_t)stream;
+    // TMA path: 16-byte aligned input rows (output rows are complex = 16 bytes per element)
+    if ((((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (ldx * 8) % 16 == 0) {
+        long long n_done = 0;
+        const int err = pfb::launch_fos_tma(x, ldx, y, ldy, coef_host, B, order, states, n, C, s, &n_done);
+        if (err) return pfb_set_error(PFB_ERR_CUDA, cudaGetErrorString((cudaError_t)err));
+        if (n_done == n) return pfb_set_error(PFB_OK, "");
+        x += n_done;          // ragged end: sequential kernel from the carried states
+        y += 2 * n_done;
+        n -= n_done;
+    }
     double *dcoef = nullptr;
     cudaError_t e = cudaMallocAsync((void **)&dcoef, (size_t)B * 3 * sizeof(double), s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dcoef, coef_host, (size_t)B * 3 * sizeof(double), cudaMemcpyHostToDevice, s);

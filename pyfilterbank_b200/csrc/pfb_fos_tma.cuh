@@ -1,0 +1,185 @@
+// pfb_fos_tma.cuh -- TMA / mbarrier kernels for the gammatone complex one-pole cascade
+// (GammatoneFilterbank.analyze / fosfilter, pyfilterbank/gammatone.py:196-237): the structure of
+// sos_tma_kernel (pfb_tma.cuh) with a different per-sample recurrence.
+//   tile row = one time chunk of one signal (JR chunks x CH signals = 32 rows); a producer warp streams
+//   [32 rows x 16 real samples] input tiles; each band warp turns its lane's row into 16 complex samples
+//   (256 bytes) in its own output tile and hands it to 4-D TMA stores; band coefficients (g, Re c, Im c)
+//   arrive in the kernel parameters (uniform registers).
+//   PASS_B = false: zero-state end states of every chunk over the band's decay window (pre-pass);
+//   sos_carry_kernel<double, ORDER> composes them with the 2*ORDER x 2*ORDER chunk transition; PASS_B = true
+//   filters every chunk from its start state and writes the bands.  With one chunk per signal there is no
+//   pre-pass and no carry.
+#pragma once
+#include "pfb_tma.cuh"
+
+namespace pfb {
+
+constexpr int kFosStages = 4;                    // input ring: 4 x [32 rows x 128 B]
+constexpr int kFosMaxBands = 7;
+
+struct FosTmaParams {
+    void *zs;             // [Q][J][2*ORDER]
+    const double *states_in;   // unused (states are read / written through `states`)
+    double *states;       // [Q][ORDER][2]
+    const int *warm;      // [B] pre-pass samples per chunk
+    long long L;
+    int Q, B, C, J, JR, CH, NW, CB, nb, G;
+};
+
+struct FosCoef {
+    double c[kCoefBytes / 24][3];   // gain, Re c, Im c per band
+};
+
+template <int ORDER>
+__device__ __forceinline__ void fos_sample(double x, double g, double cr, double ci, double (&zr)[ORDER], double (&zi)[ORDER],
+                                           double &yr, double &yi) {
+    // scipy's direct form II transposed for b = [g], a = [1, -c]:  y = z + g x ; z = c y  (g only in stage 0)
+    yr = zr[0] + g * x;
+    yi = zi[0];
+    zr[0] = cr * yr - ci * yi;
+    zi[0] = cr * yi + ci * yr;
+#pragma unroll
+    for (int s = 1; s < ORDER; ++s) {
+        yr = zr[s] + yr;
+        yi = zi[s] + yi;
+        zr[s] = cr * yr - ci * yi;
+        zi[s] = cr * yi + ci * yr;
+    }
+}
+
+template <int ORDER, bool PASS_B>
+__global__ void __launch_bounds__((kFosMaxBands + 1) * 32, PASS_B ? 2 : 4)
+fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ FosCoef tab,
+               const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+    extern __shared__ __align__(1024) char smem[];
+    constexpr int TLEN = 16;
+    constexpr int S = 2 * ORDER;
+    const int lane = threadIdx.x & 31, key = lane & 7;
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int cta = blockIdx.x;
+    const int w = cta % p.NW;
+    const int cg = cta / p.NW;
+    const int g = cg % p.G, cb = cg / p.G;
+    const int b0 = g * p.nb;
+    const int nb_here = min(p.nb, p.B - b0);
+
+    char *xs = smem;                                           // [stages][tile]
+    char *ys = smem + kFosStages * kTileBytes;                 // [nb][2][tile], output pass only
+    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (PASS_B ? p.nb : 0) * 2 * kTileBytes);
+    uint64_t *empty = full + kFosStages;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kFosStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nb_here);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long nt = p.L / TLEN;
+    long long t_first = 0;
+    if (!PASS_B) {
+        int wmax = 0;
+        for (int i = 0; i < nb_here; ++i) wmax = max(wmax, p.warm[b0 + i]);
+        long long wt = ((long long)wmax + TLEN - 1) / TLEN;
+        if (wt > nt) wt = nt;
+        t_first = nt - wt;
+    }
+    if (warp == p.nb) {
+        if (lane == 0) {
+            for (long long t = t_first; t < nt; ++t) {
+                const long long it = t - t_first;
+                const int s = (int)(it % kFosStages);
+                const unsigned ph = (unsigned)((it / kFosStages) & 1);
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], kTileBytes);
+                tma_load_3d(xs + s * kTileBytes, &xmap, &full[s], (int)(t * TLEN), p.JR * w, p.CH * cb);
+            }
+        }
+        return;
+    }
+    if (warp >= nb_here) return;
+
+    const int band = b0 + warp;
+    const int band_u = b0 + __reduce_min_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const double gain = tab.c[band_u][0], cr = tab.c[band_u][1], ci = tab.c[band_u][2];
+    const int sig = p.CH * cb + lane / p.JR;
+    const bool row_ok = sig < p.C;
+    const int q = (row_ok ? sig : 0) * p.B + band;
+    const int j = p.JR * w + lane % p.JR;
+    double zr[ORDER], zi[ORDER];
+    double *zs = reinterpret_cast<double *>(p.zs) + ((size_t)q * p.J + j) * S;
+    if (PASS_B) {
+        const double *z0 = p.J == 1 ? p.states + (size_t)q * S : zs;
+#pragma unroll
+        for (int s = 0; s < ORDER; ++s) { zr[s] = z0[2 * s]; zi[s] = z0[2 * s + 1]; }
+    } else {
+#pragma unroll
+        for (int s = 0; s < ORDER; ++s) zr[s] = zi[s] = 0.0;
+    }
+    long long t_mine = 0;
+    if (!PASS_B) {
+        const int warm = __reduce_max_sync(0xffffffffu, p.warm[band]);
+        long long wt = ((long long)warm + TLEN - 1) / TLEN;
+        if (wt > nt) wt = nt;
+        t_mine = nt - wt;
+    }
+    char *ybuf = ys + warp * 2 * kTileBytes;
+    char *yrow = ybuf + lane * kRowBytes;
+
+    long long t = t_first;
+    for (; t < t_mine; ++t) {
+        const long long it = t - t_first;
+        const int s = (int)(it % kFosStages);
+        mbar_wait(&full[s], (unsigned)((it / kFosStages) & 1));
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    for (; t < nt; ++t) {
+        const long long it = t - t_first;
+        const int s = (int)(it % kFosStages);
+        mbar_wait(&full[s], (unsigned)((it / kFosStages) & 1));
+        const char *xrow = xs + s * kTileBytes + lane * kRowBytes;
+        if (PASS_B) {
+            if (lane == 0) bulk_wait_read0();      // the previous tile's stores have read this warp's output buffer
+            __syncwarp();
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const double2 in = *reinterpret_cast<const double2 *>(xrow + ((v ^ key) << 4));
+            double yr, yi;
+            fos_sample<ORDER>(in.x, gain, cr, ci, zr, zi, yr, yi);
+            // complex sample 2 v of the tile -> output half tile (2 v) / 8, 16-byte chunk (2 v) % 8
+            if (PASS_B)
+                *reinterpret_cast<double2 *>(yrow + ((2 * v) >> 3) * kTileBytes + ((((2 * v) & 7) ^ key) << 4)) =
+                    make_double2(yr, yi);
+            fos_sample<ORDER>(in.y, gain, cr, ci, zr, zi, yr, yi);
+            if (PASS_B)
+                *reinterpret_cast<double2 *>(yrow + ((2 * v + 1) >> 3) * kTileBytes + ((((2 * v + 1) & 7) ^ key) << 4)) =
+                    make_double2(yr, yi);
+        }
+        if (PASS_B) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            if (PASS_B) {
+                tma_store_4d(&ymap, ybuf, (int)(2 * t * TLEN), p.JR * w, band, p.CH * cb);
+                tma_store_4d(&ymap, ybuf + kTileBytes, (int)(2 * t * TLEN + TLEN), p.JR * w, band, p.CH * cb);
+                bulk_commit();
+            }
+        }
+    }
+    if (PASS_B) {
+        if (lane == 0) bulk_wait0();
+        if (row_ok && j == p.J - 1) {
+            double *st = p.states + (size_t)q * S;
+#pragma unroll
+            for (int s = 0; s < ORDER; ++s) { st[2 * s] = zr[s]; st[2 * s + 1] = zi[s]; }
+        }
+    } else if (row_ok) {
+#pragma unroll
+        for (int s = 0; s < ORDER; ++s) { zs[2 * s] = zr[s]; zs[2 * s + 1] = zi[s]; }
+    }
+}
+
+}  // namespace pfb

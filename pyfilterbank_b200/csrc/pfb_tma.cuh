@@ -513,6 +513,10 @@ __global__ void __launch_bounds__(128) sos_carry_kernel(const TmaParams p) {
     }
 }
 
+// Tensor maps of the chunked signal views (pfb_api.cu).  esz_row: bytes per element of a row (8 / 4); `L`, `ld` in elements.
+bool make_x_map(CUtensorMap *map, int dtype, const void *base, long long L, int J, long long C, long long ld, int JR, int CH);
+bool make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int B, long long C, long long ld, int JR, int CH);
+
 // ev: null, or 4 events recorded before the pre-pass and after each of the three kernels
 // phases: 1 = pre-pass, 2 = carry + output pass, 3 = all (on stream s)
 int launch_tma_dd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,

@@ -201,3 +201,32 @@ def test_weighted_bank_golden(pfb):
     ofe = pfb.FractionalOctaveFilterbank(sample_rate=48000, filterfun='exact')
     y, st, _ = ofe.filter_mimo_c(g["x"], weighting="A")
     assert np.array_equal(y, g["y_A"]) and np.array_equal(st, g["states_A"])
+
+
+@pytest.mark.parametrize("J", [0, 1, 2, 8, 32, 64])
+def test_gammatone_tma_tile_shapes(pfb, oracle, J, monkeypatch):
+    """The TMA kernels of the gammatone bank: every tile shape (J chunks per signal, J = 0: planner's choice),
+    ragged batch sizes and lengths, carried states over two calls, against the oracle's scipy-order cascade."""
+    from pyfilterbank_b200 import gammatone as gt
+    if J:
+        monkeypatch.setenv("PFB_FOS_J", str(J))
+    gfb = pfb.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
+    rng = np.random.default_rng(40 + J)
+    for C, n in ((1, 20000), (5, 16000 + 6), (40, 9000)):
+        if J and n // J < 64:
+            continue
+        x = rng.standard_normal((C, n))
+        xt = torch.from_numpy(x).cuda()
+        y, st = gt.fos_bank(xt, gfb._coef_rows, 4)
+        cut = 4096 + 2
+        ya, sa = gt.fos_bank(xt[:, :cut].contiguous(), gfb._coef_rows, 4)
+        yb, sb = gt.fos_bank(xt[:, cut:].contiguous(), gfb._coef_rows, 4, sa)
+        y2 = torch.cat([ya, yb], dim=2)
+        for i in (0, 17, 63):
+            b, a = gfb._coeffs[i]
+            for c in sorted({0, C - 1}):
+                y0, s0 = oracle.fosfilter(b, a, 4, x[c])
+                assert rel_l2(y[c, i].cpu().numpy(), y0) <= 1e-11, (C, n, i, c, rel_l2(y[c, i].cpu().numpy(), y0))
+                assert rel_l2(st[c, i].cpu().numpy(), s0) <= 1e-10
+                assert rel_l2(y2[c, i].cpu().numpy(), y0) <= 1e-11
+                assert rel_l2(sb[c, i].cpu().numpy(), s0) <= 1e-10
