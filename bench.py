@@ -52,55 +52,89 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread every 5 ms
+    (nvidia_ml_py), falling back to an `nvidia-smi -lms` subprocess."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []          # (time, sm_mhz, reasons bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.smmax = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(clk), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "smi"
+
+            def read():
+                for line in self.proc.stdout:
+                    f = [v.strip() for v in line.split(",")]
+                    try:
+                        self.smmax = float(f[1])
+                        self.samples.append((time.time(), float(f[0]), int(f[2], 16)))
+                    except Exception:
+                        pass
+            self.thread = threading.Thread(target=read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.mode = None
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smmax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                clk, mx = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            smmax = mx
-            if t0 - 0.05 <= ts <= t1 + 0.05:
-                sm.append(clk)
-                for n, v in zip(names, f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        if not sm:   # region shorter than the sampling period: use the nearest samples
-            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) > 2]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.mode == "smi":
+            time.sleep(0.1)
+            self.proc.terminate()
+        elif self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.smmax, "reasons": ["no clock samples (%s)" % self.mode],
+                    "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:   # region shorter than the sampling period: nearest samples
+            inside = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[:3]
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = sorted(n for n, bit in self.BAD.items() if mask & bit)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": self.smmax, "reasons": reasons,
+                "samples": len(inside), "source": self.mode}
 
 
 def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
@@ -153,7 +187,7 @@ def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
