@@ -91,6 +91,15 @@ PFB_API void pfb_bank_destroy(pfb_bank *bank);
 PFB_API int pfb_bank_filter(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
                     void *states, int64_t n, int C, int flags, void *stream);
 
+/* Band-level epilogue: the band signals are reduced to energies in the kernel instead of being written --
+ * levels[(c * B + b) * ld_levels + k] = sum of y[c][b][t]^2 over block k = [k * block_len, (k + 1) * block_len)
+ * (what the reference's users compute from filter_mimo_c's output, `L = 10*log10(sum(y**2))`, octbank.py:262-263,
+ * :536-537).  No band signal touches HBM.  DEVICE pointers, asynchronous on `stream`; shared banks only;
+ * n must be a multiple of block_len and block_len a multiple of 32 (float64) / 64 (float32) samples.
+ * States are carried like in pfb_bank_filter. */
+PFB_API int pfb_bank_levels(pfb_bank *bank, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
+                            void *states, int64_t n, int C, int64_t block_len, int flags, void *stream);
+
 /* Same on HOST buffers (pageable or pinned): streams the signal through the device in time blocks
  * with carried states, overlapping H2D, kernels and D2H.  Synchronous. */
 PFB_API int pfb_bank_filter_host(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,

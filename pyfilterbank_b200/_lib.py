@@ -41,6 +41,8 @@ def lib():
         L.pfb_bank_destroy.restype = None
         L.pfb_bank_filter.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci, vp]
         L.pfb_bank_filter.restype = ci
+        L.pfb_bank_levels.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, i64, ci, vp]
+        L.pfb_bank_levels.restype = ci
         L.pfb_bank_filter_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci]
         L.pfb_bank_filter_host.restype = ci
         L.pfb_bank_last_launch.argtypes = [vp, ctypes.POINTER(LaunchInfo)]
@@ -114,6 +116,9 @@ class Bank:
 
     def filter_ptr(self, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags=0, stream=0):
         check(lib().pfb_bank_filter(self._h, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags, stream))
+
+    def levels_ptr(self, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags=0, stream=0):
+        check(lib().pfb_bank_levels(self._h, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags, stream))
 
     def filter_host(self, dtype, x, ldx, y, ldy, states, n, C, flags=0):
         check(lib().pfb_bank_filter_host(self._h, dtype, x.ctypes.data, ldx, y.ctypes.data, ldy,

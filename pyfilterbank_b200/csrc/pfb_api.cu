@@ -430,6 +430,133 @@ bool pfb::make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J
     return r == CUDA_SUCCESS;
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA path helpers (pfb_tma.cuh): band grouping, tile-shape cost model, one launch set.
+// ------------------------------------------------------------------------------------------------
+static void tma_bands(const pfb_bank *b, int *nb, int *G) {
+    int nbmax = env_int("PFB_TMA_NB", pfb::kTmaSmallBands);
+    nbmax = std::max(1, std::min(nbmax, pfb::kTmaMaxBands));
+    const int G0 = (b->B + nbmax - 1) / nbmax;
+    *nb = (b->B + G0 - 1) / G0;
+    *G = (b->B + *nb - 1) / *nb;
+}
+
+// Tile shape: J chunks per cascade, a tile's 32 rows = JR chunks x CH channels.  Candidates: J = 1, 2, .. 16
+// (JR = J, CH = 32 / J) and J = 32 g (JR = 32, CH = 1), at most jmax.  Cost model: output pass / wave efficiency
+// of its grid, plus the pre-pass share estimated from the bands' decay lengths.
+static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int G, long long jmax) {
+    int J = env_int("PFB_TMA_J", 0);
+    if (env_int("PFB_TMA_GROUPS", 0) > 0) J = 32 * env_int("PFB_TMA_GROUPS", 0);
+    if (J > 0 && J <= jmax) return J;
+    J = 1;
+    if (b->wproxy.empty()) {   // decay length of every band (pre-pass window if chunks were unbounded)
+        b->wproxy.resize(b->B);
+        for (int r = 0; r < b->B; ++r)
+            b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20, arith64 ? 1e-11 : 1e-8);
+    }
+    const double slots = 2.0 * b->sm_count;
+    double best = 1e300;
+    for (int cand = 0; cand < 13; ++cand) {
+        const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
+        const int jr = std::min(j, 32), chn = 32 / jr;
+        if (j > jmax) break;
+        if (n / j / tt * tt < (j > 1 ? 64LL : 4LL) * tt && j > 1) break;
+        const long long cb = (C + chn - 1) / chn;
+        const double ctas = (double)cb * G * (j / jr);
+        const double waves = ctas / slots;
+        double eff = waves >= 1 ? waves / std::ceil(waves) : waves;
+        eff *= (double)C / (double)(cb * chn);                         // ragged channel blocks idle lanes
+        double share = 0;
+        if (j > 1)
+            for (int r = 0; r < b->B; ++r) share += std::min((double)j * b->wproxy[r], (double)n);
+        share /= (double)b->B * (double)n;
+        const double cost = (1.0 + 0.4 * share) / eff;
+        if (cost < best) best = cost, J = j;
+    }
+    return J;
+}
+
+// One (pre-pass, carry, output | levels) launch set over J chunks of Lt samples.  Caller holds b->mu.
+static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long long ldx, void *y, long long ldy, void *states,
+                   long long Lt, int J, int C, int nb, int G, cudaStream_t stream, double *levels, long long lev_ld,
+                   long long lev_off, int ut, bool may_time) {
+    const int arith = arith64 ? PFB_F64 : PFB_F32;
+    const int tt = 2 * pfb::kRowBytes / (dtype == PFB_F64 ? 8 : 4);
+    const int JR = std::min(J, 32), CH = 32 / JR;
+    const int Q = C * b->B;
+    const Tables *tab = nullptr;
+    if (J > 1) {
+        int rc = ensure_tables(b, arith, Lt, tt, &tab);
+        if (rc) return rc;
+    }
+    const size_t asz = arith64 ? 8 : 4;
+    // chunk-state scratch: kept per (bank, stream) so repeated calls do not allocate
+    const size_t need = (size_t)Q * J * 2 * b->K * asz;
+    auto &ws = b->workspace[(void *)stream];
+    if (ws.second < need) {
+        if (ws.first) {
+            PFB_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(ws.first);
+            ws = {nullptr, 0};
+        }
+        PFB_CUDA(cudaMalloc(&ws.first, need));
+        ws.second = need;
+    }
+    const bool timed = may_time && b->timing_left > 0;
+    if (timed) { --b->timing_left; ++b->timing_calls; }
+    CUtensorMap xmap, ymap;
+    if (!pfb::make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH)) return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (y) {
+        if (!pfb::make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH)) return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    } else {
+        ymap = xmap;   // band-level epilogue: nothing is stored through it
+    }
+    pfb::TmaParams tp{};
+    tp.zs = ws.first;
+    tp.states = states;
+    tp.L = Lt;
+    tp.Q = Q, tp.B = b->B, tp.C = C, tp.J = J, tp.nb = nb, tp.G = G;
+    tp.JR = JR, tp.CH = CH, tp.NW = J / JR, tp.CB = (C + CH - 1) / CH;
+    tp.Ktot = b->K, tp.k0 = 0;
+    tp.nb_a = nb;
+    tp.levels = levels, tp.lev_ld = lev_ld, tp.lev_off = lev_off, tp.ut = ut;
+    if (tab) {
+        tp.P = tab->P[0];
+        tp.warm = tab->warm[0];
+        tp.gains = tab->gains;
+        tp.H = tab->H;
+        tp.Hoff = tab->Hoff;
+        // the GEMM-form pre-pass balances best with 4 bands per CTA (sweep in profiles/)
+        tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", tab->H ? 4 : nb), nb));
+    } else {
+        tp.gains = b->gains_only(arith);   // single chunk: no transition / pre-pass tables needed
+    }
+    tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (timed)
+        for (cudaEvent_t &e : ev) e = b->tev_new();
+    int launches = 0;
+    const double *ch = b->coef_host.data();
+    int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
+              : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
+                              : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3);
+    if (err != 0) return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+    if (timed) {
+        b->trecs.push_back({ev[0], ev[1], 0});
+        b->trecs.push_back({ev[1], ev[2], 1});
+        b->trecs.push_back({ev[2], ev[3], 2});
+        b->trecs.push_back({ev[0], ev[3], 3});
+    }
+    b->last = pfb_launch_info{};
+    b->last.mode = PFB_MODE_SCAN;
+    b->last.kernels = launches;
+    b->last.warps_per_cascade = J / JR;
+    b->last.chunk = Lt;
+    b->last.warm_total = tab ? tab->warm_total * C : 0;
+    b->last.aligned = 2;   // 2 = TMA path
+    return PFB_OK;
+}
+
 int pfb_set_error(int status, const char *msg) {   // used by the other translation units
     g_status = status;
     g_error = msg ? msg : "";
@@ -620,129 +747,28 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     long long L = n;
     const Tables *tab = nullptr;
     if (mode == PFB_MODE_SCAN && tma_ok) {
-        int nbmax = env_int("PFB_TMA_NB", pfb::kTmaSmallBands);
-        nbmax = std::max(1, std::min(nbmax, pfb::kTmaMaxBands));
-        const int G0 = (b->B + nbmax - 1) / nbmax;
-        const int nb = (b->B + G0 - 1) / G0;
-        const int G = (b->B + nb - 1) / nb;
-        // Tile shape: J chunks per cascade, a tile's 32 rows = JR chunks x CH channels.  Candidates: J = 1, 2, .. 16
-        // (JR = J, CH = 32 / J) and J = 32 g (JR = 32, CH = 1).  Cost model: output pass / wave efficiency of its
-        // grid, plus the pre-pass share estimated from the bands' decay lengths.
-        int J = env_int("PFB_TMA_J", 0), JR = 0, CH = 0;
-        if (env_int("PFB_TMA_GROUPS", 0) > 0) J = 32 * env_int("PFB_TMA_GROUPS", 0);
-        if (J <= 0) {
-            if (b->wproxy.empty()) {   // decay length of every band (pre-pass window if chunks were unbounded)
-                b->wproxy.resize(b->B);
-                for (int r = 0; r < b->B; ++r)
-                    b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20,
-                                                       arith64 ? 1e-11 : 1e-8);
-            }
-            const double slots = 2.0 * b->sm_count;
-            double best = 1e300;
-            for (int cand = 0; cand < 13; ++cand) {
-                const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
-                const int jr = std::min(j, 32), chn = 32 / jr;
-                if (n / j / tt * tt < (j > 1 ? 64LL : 4LL) * tt && j > 1) break;
-                const long long cb = (C + chn - 1) / chn;
-                const double ctas = (double)cb * G * (j / jr);
-                const double waves = ctas / slots;
-                double eff = waves >= 1 ? waves / std::ceil(waves) : waves;
-                eff *= (double)C / (double)(cb * chn);                         // ragged channel blocks idle lanes
-                double share = 0;
-                if (j > 1)
-                    for (int r = 0; r < b->B; ++r) share += std::min((double)j * b->wproxy[r], (double)n);
-                share /= (double)b->B * (double)n;
-                const double cost = (1.0 + 0.4 * share) / eff;
-                if (cost < best) best = cost, J = j;
-            }
-        }
-        JR = std::min(J, 32);
-        CH = 32 / JR;
-        if (JR * CH != 32 || J % JR != 0) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad chunk count %d", J);
-        const int groups = J / JR;
+        int nb, G;
+        tma_bands(b, &nb, &G);
+        const int J = tma_pick_J(b, n, C, tt, arith64, G, 1 << 30);
+        const int JR = std::min(J, 32);
+        if (J <= 0 || J % JR != 0 || 32 % JR != 0) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad chunk count %d", J);
         const long long Lt = n / J / tt * tt;
         if (Lt >= 4LL * tt && Lt < 0x7fffffffLL) {
-            if (J > 1) {
-                rc = ensure_tables(b, arith, Lt, tt, &tab);
-                if (rc) return rc;
-            }
             const long long n_main = Lt * J;
-            {
-                const size_t asz = arith64 ? 8 : 4;
-                // chunk-state scratch: kept per (bank, stream) so repeated calls do not allocate
-                const size_t need = (size_t)Q * J * 2 * b->K * asz;
-                auto &ws = b->workspace[(void *)stream];
-                if (ws.second < need) {
-                    if (ws.first) {
-                        PFB_CUDA(cudaStreamSynchronize(stream));
-                        cudaFree(ws.first);
-                        ws = {nullptr, 0};
-                    }
-                    PFB_CUDA(cudaMalloc(&ws.first, need));
-                    ws.second = need;
-                }
-                void *zs = ws.first;
-                const bool timed = b->timing_left > 0;
-                if (timed) { --b->timing_left; ++b->timing_calls; }
-                CUtensorMap xmap, ymap;
-                if (!pfb::make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH) ||
-                    !pfb::make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH))
-                    return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-                pfb::TmaParams tp{};
-                tp.zs = zs;
-                tp.states = states;
-                tp.L = Lt;
-                tp.Q = Q, tp.B = b->B, tp.C = C, tp.J = J, tp.nb = nb, tp.G = G;
-                tp.JR = JR, tp.CH = CH, tp.NW = J / JR, tp.CB = (C + CH - 1) / CH;
-                tp.Ktot = b->K, tp.k0 = 0;
-                tp.nb_a = nb;
-                if (tab) {
-                    tp.P = tab->P[0];
-                    tp.warm = tab->warm[0];
-                    tp.gains = tab->gains;
-                    tp.H = tab->H;
-                    tp.Hoff = tab->Hoff;
-                    // the GEMM-form pre-pass balances best with 4 bands per CTA (sweep in profiles/)
-                    tp.nb_a = std::max(1, std::min(env_int("PFB_TMA_NB_A", tab->H ? 4 : nb), nb));
-                } else {
-                    tp.gains = b->gains_only(arith);   // single chunk: no transition / pre-pass tables needed
-                }
-                tp.G_a = (b->B + tp.nb_a - 1) / tp.nb_a;
-                cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-                if (timed)
-                    for (cudaEvent_t &e : ev) e = b->tev_new();
-                int launches = 0;
-                const double *ch = b->coef_host.data();
-                int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
-                          : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
-                                          : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3);
-                if (err != 0)
-                    return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
-                if (timed) {
-                    b->trecs.push_back({ev[0], ev[1], 0});
-                    b->trecs.push_back({ev[1], ev[2], 1});
-                    b->trecs.push_back({ev[2], ev[3], 2});
-                    b->trecs.push_back({ev[0], ev[3], 3});
-                }
-                pfb_launch_info main_info{};
-                main_info.mode = PFB_MODE_SCAN;
-                main_info.kernels = launches;
-                main_info.warps_per_cascade = groups;
-                main_info.chunk = Lt;
-                main_info.warm_total = tab ? tab->warm_total * C : 0;
-                main_info.aligned = 2;   // 2 = TMA path
-                if (n_main < n) {        // the ragged end continues from the carried states
-                    b->mu.unlock();
-                    rc = pfb_bank_filter(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
-                                         states, n - n_main, C, (flags & ~PFB_MODE_MASK) | 0x100 | PFB_MODE_AUTO, stream_);
-                    b->mu.lock();
-                    if (rc) return rc;
-                    main_info.kernels += b->last.kernels;
-                }
-                b->last = main_info;
-                g_status = PFB_OK;
-                return PFB_OK;
+            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true);
+            if (rc) return rc;
+            pfb_launch_info main_info = b->last;
+            if (n_main < n) {        // the ragged end continues from the carried states
+                b->mu.unlock();
+                rc = pfb_bank_filter(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
+                                     states, n - n_main, C, (flags & ~PFB_MODE_MASK) | 0x100 | PFB_MODE_AUTO, stream_);
+                b->mu.lock();
+                if (rc) return rc;
+                main_info.kernels += b->last.kernels;
             }
+            b->last = main_info;
+            g_status = PFB_OK;
+            return PFB_OK;
         }
     }
     if (mode == PFB_MODE_SCAN) {
@@ -918,6 +944,72 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
     g_status = PFB_OK;
     return PFB_OK;
 #undef PFB_CUDA_C
+}
+
+int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels, void *states,
+                    int64_t n, int C, int64_t block_len, int flags, void *stream_) {
+    if (!b || !x || !levels || !states) return fail(PFB_ERR_INVALID, "pfb_bank_levels: null argument");
+    if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_levels: bad dtype %d", dtype);
+    const int esz = dtype == PFB_F64 ? 8 : 4;
+    const int tt = 2 * pfb::kRowBytes / esz;
+    const bool arith64 = dtype == PFB_F64 || (flags & PFB_ARITH_F64);
+    if (n <= 0 || C <= 0 || ldx < n || block_len <= 0 || n % block_len != 0 || block_len % tt != 0 ||
+        ld_levels < n / block_len)
+        return fail(PFB_ERR_INVALID,
+                    "pfb_bank_levels: n (%lld) must be a multiple of block_len (%lld), block_len a multiple of %d samples",
+                    (long long)n, (long long)block_len, tt);
+    if (b->per_channel || b->sweeps.size() != 1 || !aligned16(x) || (ldx * esz) % 16 != 0 ||
+        b->B * b->K > (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections))
+        return fail(PFB_ERR_INVALID, "pfb_bank_levels: needs a shared bank with K in {1,2,3,4,6,8} and 16-byte aligned rows");
+    if ((long long)C * b->B > 0x7fffffffLL) return fail(PFB_ERR_INVALID, "pfb_bank_levels: C*B too large");
+    std::lock_guard<std::mutex> lock(b->mu);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long nblocks = n / block_len, Q = (long long)C * b->B;
+    // energy unit: block_len / r, r the smallest divisor of block_len / tt that gives enough units to cut into chunks
+    long long r = 1;
+    const long long bt = block_len / tt;
+    for (long long d = 1; d <= bt; ++d) {
+        if (bt % d) continue;
+        r = d;
+        if (nblocks * d >= 512 || block_len / d < 8LL * tt) break;
+    }
+    const long long unit = block_len / r, nunits = nblocks * r;
+    double *partial = levels;
+    long long pld = ld_levels;
+    if (r > 1) {
+        PFB_CUDA(cudaMallocAsync((void **)&partial, (size_t)Q * nunits * sizeof(double), stream));
+        pld = nunits;
+    }
+    int nb, G;
+    tma_bands(b, &nb, &G);
+    const long long min_units = (4LL * tt + unit - 1) / unit;   // a chunk is at least four tile steps
+    long long pos = 0;
+    int kernels = 0;
+    while (pos < nunits) {
+        const long long rem = nunits - pos;
+        int J = tma_pick_J(b, rem * unit, C, tt, arith64, G, std::max<long long>(1, rem / min_units));
+        if (J > rem) J = 1;
+        const int JR = std::min(J, 32);
+        if (J % JR != 0 || 32 % JR != 0) J = 1;
+        const long long Lu = rem / J;
+        if (Lu * unit >= 0x7fffffffLL) return fail(PFB_ERR_INVALID, "pfb_bank_levels: signal too long for one call");
+        int rc = tma_run(b, dtype, arith64, (const char *)x + pos * unit * esz, ldx, nullptr, 0, states, Lu * unit, J, C, nb, G,
+                         stream, partial, pld, pos, (int)(unit / tt), pos == 0);
+        if (rc) return rc;
+        kernels += b->last.kernels;
+        pos += (long long)J * Lu;
+    }
+    if (r > 1) {
+        const long long total = Q * nblocks;
+        pfb::levels_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, pld, levels, ld_levels, nblocks,
+                                                                                       (int)r, Q);
+        ++kernels;
+        PFB_CUDA(cudaGetLastError());
+        PFB_CUDA(cudaFreeAsync(partial, stream));
+    }
+    b->last.kernels = kernels;
+    g_status = PFB_OK;
+    return PFB_OK;
 }
 
 int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,

@@ -62,12 +62,14 @@ static int run_scan(const SosParams &p, int warps, const double *coef_host, int 
 template <int K, int NBMAX, bool SCALED>
 static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
                       cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
-    auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, false, NBMAX, SCALED>;
-    auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, true, NBMAX, SCALED>;
+    auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, 0, NBMAX, SCALED>;
+    auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED>;
+    auto kern_l = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED>;
     const int smem_a = kTmaStages * 2 * kTileBytes + 2 * kTmaStages * 8;
     const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 2 * kTmaStages * 8;
     cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e != cudaSuccess) return (int)e;
     static thread_local CoefTable<PFB_A> tab;
     for (int r = 0; r < p.B; ++r) {
@@ -110,7 +112,8 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             *launches += 1;
         }
         if (ev) cudaEventRecord(ev[2], s);
-        kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+        if (p.levels) kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap);   // energies instead of band signals
+        else kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
         if (ev) cudaEventRecord(ev[3], s);
         *launches += 1;
     }

@@ -51,6 +51,11 @@ struct TmaParams {
     // (lane l <-> state 8 mt + l / 4, sample l % 4); Hoff[b]: band b's offset in doubles; null: recurrence pre-pass.
     const double *H;
     const long long *Hoff;
+    // Band-level (energy) epilogue instead of the output store: sums of y^2 per `ut` tiles, written time-ordered to
+    // levels[q * lev_ld + lev_off + j * (L / unit) + u]  (unit = ut tile steps; chunk j, unit u of the chunk)
+    double *levels;
+    long long lev_ld, lev_off;
+    int ut;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -109,10 +114,13 @@ __device__ __forceinline__ A scaled_step(A x, const A *c, A &w1, A &w2) {
     return y;
 }
 
-// Filter one 128-byte half tile: x row read from the shared input tile, result written to the warp's
-// own output tile (same swizzled layout).  STORE = false: pre-pass, nothing is written.
-template <typename T, typename A, int K, bool STORE, bool SCALED>
-__device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int key, const A (&c)[K][5], A (&w)[K][2]) {
+// Filter one 128-byte half tile: x row read from the shared input tile.  MODE 1: result written to the warp's
+// own output tile (same swizzled layout); MODE 0: pre-pass, nothing is written; MODE 2: the squares of the
+// (output-type rounded) results are added to `acc` (band-level epilogue).
+template <typename T, typename A, int K, int MODE, bool SCALED>
+__device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int key, const A (&c)[K][5], A (&w)[K][2],
+                                            A *acc = nullptr) {
+    constexpr bool STORE = MODE == 1;
     using V = typename Vec16<T>::type;
     constexpr int EPV = Vec16<T>::N;
     constexpr int kBatch = PFB_ROW_BATCH;
@@ -132,6 +140,10 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
                     s = SCALED ? scaled_step<A>(s, c[k], w[k][0], w[k][1]) : Biquad<A, false>::step(s, c[k], w[k][0], w[k][1]);
                 if (SCALED) s *= c[0][0];
                 e[i] = (T)s;
+                if (MODE == 2) {
+                    const A r = (A)e[i];
+                    *acc = fma(r, r, *acc);
+                }
             }
         }
         if (STORE) {
@@ -143,10 +155,13 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
 
 // cta = ((cb * G) + g) * NW + w : channel block cb, band group g, chunk group w.
 // Tile row r <-> chunk JR * w + r % JR of channel CH * cb + r / JR.
-// PASS_B = false: pre-pass, writes zero-state chunk end states to zs; true: output pass from zs.
-template <typename T, typename A, int K, bool PASS_B, bool SCALED>
+// PASS 0: pre-pass, writes zero-state chunk end states to zs; 1: output pass from zs; 2: like 1 but the band
+// signals are reduced to energies per time unit instead of being stored (band-level epilogue).
+template <typename T, typename A, int K, int PASS, bool SCALED>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
                                         const CUtensorMap &ymap, char *smem, int cta, int ch0) {
+    constexpr bool PASS_B = PASS != 0;
+    constexpr bool STORE_Y = PASS == 1;
     constexpr int TLEN = kRowBytes / (int)sizeof(T);      // samples per 128-byte half row
     constexpr int TT = 2 * TLEN;                          // samples per tile step (256-byte rows)
     constexpr int S = 2 * K;
@@ -165,7 +180,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 
     char *xs = smem;                                          // [stages][2][tile]
     char *ys = smem + kTmaStages * kStageBytes;               // [nb][2][tile], output pass only
-    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (PASS_B ? p.nb : 0) * kStageBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb : 0) * kStageBytes);
     uint64_t *empty = full + kTmaStages;
 
     if (threadIdx.x == 0) {
@@ -247,7 +262,29 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     char *ybuf = ys + warp * kStageBytes;
     char *yrow = ybuf + lane * kRowBytes;
 
-    if (PASS_B) {
+    if (PASS == 2) {
+        double acc_unit = 0.0;
+        int tcount = 0;
+        double *lev = p.levels + (size_t)q * p.lev_ld + p.lev_off + (long long)j * (nt / p.ut);
+        for (long long t = 0; t < nt; ++t) {
+            const int s = (int)(t % kTmaStages);
+            const unsigned ph = (unsigned)((t / kTmaStages) & 1);
+            mbar_wait(&full[s], ph);
+            const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+            A acc = A(0);
+            filter_half<T, A, K, 2, SCALED>(xrow, nullptr, key, c, wst, &acc);
+            filter_half<T, A, K, 2, SCALED>(xrow + kTileBytes, nullptr, key, c, wst, &acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            acc_unit += (double)acc;
+            if (++tcount == p.ut) {
+                if (row_ok) *lev = acc_unit;
+                ++lev;
+                acc_unit = 0.0;
+                tcount = 0;
+            }
+        }
+    } else if (PASS_B) {
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % kTmaStages);
             const unsigned ph = (unsigned)((t / kTmaStages) & 1);
@@ -259,8 +296,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             // arrive as two separate 128-byte bursts; see profiles/r01_ubench_tma_store_rows.txt.)
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
-            filter_half<T, A, K, true, SCALED>(xrow, yrow, key, c, wst);
-            filter_half<T, A, K, true, SCALED>(xrow + kTileBytes, yrow + kTileBytes, key, c, wst);
+            filter_half<T, A, K, 1, SCALED>(xrow, yrow, key, c, wst);
+            filter_half<T, A, K, 1, SCALED>(xrow + kTileBytes, yrow + kTileBytes, key, c, wst);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -284,14 +321,14 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const int s = (int)(it % kTmaStages);
             mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            filter_half<T, A, K, false, SCALED>(xrow, nullptr, key, c, wst);
-            filter_half<T, A, K, false, SCALED>(xrow + kTileBytes, nullptr, key, c, wst);
+            filter_half<T, A, K, 0, SCALED>(xrow, nullptr, key, c, wst);
+            filter_half<T, A, K, 0, SCALED>(xrow + kTileBytes, nullptr, key, c, wst);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
     }
     if (PASS_B) {
-        if (lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
+        if (STORE_Y && lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
         if (row_ok && j == p.J - 1) {    // the last chunk ends with the cascade's final state
             A *st = reinterpret_cast<A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2;
 #pragma unroll
@@ -469,12 +506,12 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
 
 // The pre-pass needs no output tiles and few registers: it is compiled for 4 resident CTAs per SM
 // (which also makes ptxas keep the coefficients in uniform registers), the output pass for 2.
-template <typename T, typename A, int K, bool PASS_B, int NBMAX, bool SCALED>
-__global__ void __launch_bounds__((NBMAX + 1) * 32, PASS_B ? 2 : 4)
+template <typename T, typename A, int K, int PASS, int NBMAX, bool SCALED>
+__global__ void __launch_bounds__((NBMAX + 1) * 32, PASS == 1 ? 2 : PASS == 2 ? 3 : 4)
 sos_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
                const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
     extern __shared__ __align__(1024) char smem[];
-    tma_cta<T, A, K, PASS_B, SCALED>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
+    tma_cta<T, A, K, PASS, SCALED>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
 }
 
 // Carry between the two passes: per cascade, s[0] = carried-in state, s[j+1] = P s[j] + z[j];
@@ -511,6 +548,18 @@ __global__ void __launch_bounds__(128) sos_carry_kernel(const TmaParams p) {
         for (int m = 0; m < S; ++m) acc = fma(prow[m], __shfl_sync(0xffffffffu, s, base + m), acc);
         s = acc;
     }
+}
+
+// levels[q][k] = sum of r consecutive unit energies partial[q][k r .. k r + r), fixed order (deterministic)
+static __global__ void levels_reduce_kernel(const double *partial, long long pld, double *levels, long long lld, long long nblocks,
+                                     int r, long long Q) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Q * nblocks) return;
+    const long long q = i / nblocks, k = i - q * nblocks;
+    const double *src = partial + q * pld + k * r;
+    double acc = 0.0;
+    for (int u = 0; u < r; ++u) acc += src[u];
+    levels[q * lld + k] = acc;
 }
 
 // Tensor maps of the chunked signal views (pfb_api.cu).  esz_row: bytes per element of a row (8 / 4); `L`, `ld` in elements.

@@ -268,6 +268,34 @@ class FractionalOctaveFilterbank:
         return y.cpu().numpy() if isinstance(y, torch.Tensor) else y, \
             st.cpu().numpy() if isinstance(st, torch.Tensor) else st, wst.cpu().numpy()
 
+    def filter_levels(self, x, block_len=None, states=None, db=False):
+        """Band energies without the band signals (opt-in; the reference's users compute
+        `10*log10(sum(y**2))` from filter_mimo_c's output, octbank.py:262-263): x (N,) or (N, C) ->
+        (energy (N // block_len, B, C), flat states like filter_mimo_c).  The squares are summed inside
+        the filtering kernel, so nothing of size N*B*C is written.  N must be a multiple of block_len
+        (None: the whole signal) and block_len of 32 samples.  db=True returns 10*log10(energy)."""
+        on_device = isinstance(x, torch.Tensor) and x.is_cuda
+        if on_device:
+            sig = x.detach().to(torch.float64)
+        else:
+            sig = torch.from_numpy(np.array(x, dtype=np.float64)).to(_sf._device())
+        n = sig.shape[0]
+        rows = sig.reshape(n, -1).t().contiguous()
+        C, B, K = rows.shape[0], self.num_bands, self.order
+        bank = _sf.get_bank(np.ascontiguousarray(self.sosmat.T).reshape(B, K, 6))
+        st = None
+        if states is not None:
+            st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.array(states, dtype=np.float64))
+            st = st.to(device=rows.device, dtype=torch.float64).reshape(C, B, K, 2).clone()
+        e, st = _sf.bank_levels(bank, rows, block_len, st)
+        e = e.permute(2, 1, 0)
+        if db:
+            e = 10.0 * torch.log10(e)
+        st = st.reshape(-1)
+        if on_device:
+            return e, st
+        return e.cpu().numpy(), st.cpu().numpy()
+
     def filter(self, x, ffilt=False, states=None):
         """Single-channel filtering, octbank.py:436-476: returns (y (N, B) float64, dict
         {centre frequency: states (2K,)}).  The B per-band cascades of the reference's loop run as

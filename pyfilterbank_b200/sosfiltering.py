@@ -17,8 +17,8 @@ import torch
 from . import _lib
 from ._lib import Bank
 
-__all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "bank_filter", "bilinear_sos",
-           "get_bank"]
+__all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "bank_filter", "bank_levels",
+           "bilinear_sos", "get_bank"]
 
 _bank_cache = collections.OrderedDict()
 
@@ -76,6 +76,32 @@ def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False
                         states.data_ptr(), N, C, _lib.flags_of(mode, exact, arith64, decimate),
                         torch.cuda.current_stream().cuda_stream)
     return out, states
+
+
+def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
+    """Band energies of x (C, N) CUDA tensor through `bank` without materialising the band signals:
+    returns (energy (C, B, N // block_len) float64 = sum of y^2 per block, states).  block_len=None: one
+    block = the whole signal.  N must be a multiple of block_len, block_len of 32 (float64) / 64 (float32)."""
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a (C, N) CUDA tensor with contiguous rows")
+    C, N = x.shape
+    if x.dtype == torch.float64:
+        dtype, sdt = _lib.PFB_F64, torch.float64
+    elif x.dtype == torch.float32:
+        dtype, sdt = _lib.PFB_F32, (torch.float64 if arith64 else torch.float32)
+    else:
+        raise ValueError("x must be float32 or float64")
+    block_len = N if block_len is None else int(block_len)
+    B, K = bank.B, bank.K
+    if states is None:
+        states = torch.zeros((C, B, K, 2), dtype=sdt, device=x.device)
+    nblocks = N // block_len if block_len > 0 else 0
+    out = torch.empty((C, B, max(nblocks, 1)), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        bank.levels_ptr(dtype, x.data_ptr(), x.stride(0) if C > 1 else max(N, 1), out.data_ptr(), out.stride(1),
+                        states.data_ptr(), N, C, block_len, _lib.flags_of("auto", False, arith64),
+                        torch.cuda.current_stream().cuda_stream)
+    return out[:, :, :nblocks], states
 
 
 def _sos_rows(sos):

@@ -230,3 +230,56 @@ def test_gammatone_tma_tile_shapes(pfb, oracle, J, monkeypatch):
                 assert rel_l2(st[c, i].cpu().numpy(), s0) <= 1e-10
                 assert rel_l2(y2[c, i].cpu().numpy(), y0) <= 1e-11
                 assert rel_l2(sb[c, i].cpu().numpy(), s0) <= 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# band-level epilogue (SURVEY.md section 8 f, rank 1): energies computed inside the filtering kernel
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("C,n,block", [(3, 48000, 4800), (1, 40960, None), (70, 6400, 640), (2, 96000, 32)])
+def test_bank_levels_vs_oracle(pfb, oracle, C, n, block):
+    rng = np.random.default_rng(C + n)
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000)
+    x = rng.standard_normal((n, C))
+    B = ofb.num_bands
+    sos = np.ascontiguousarray(ofb.sosmat.T).reshape(B, 4, 6)
+    y0, s0 = oracle.sos_bank(x.T, sos)                                  # (C, B, n)
+    bl = n if block is None else block
+    e0 = (y0.reshape(C, B, n // bl, bl) ** 2).sum(axis=3).transpose(2, 1, 0)
+    e, st = ofb.filter_levels(x, block_len=block)
+    assert e.shape == (n // bl, B, C)
+
+    def close(a):
+        # per block relative to the band's largest block energy (short blocks can hold almost no energy, and
+        # the first blocks of the low bands are the filter's onset), and per (band, channel) in L2 over blocks
+        scale = e0.max(axis=0, keepdims=True)
+        return np.max(np.abs(a - e0) / scale) <= 2e-9 and \
+            np.max(np.linalg.norm(a - e0, axis=0) / np.linalg.norm(e0, axis=0)) <= 1e-9
+    assert close(e)
+    assert rel_l2(st, s0.reshape(-1)) <= 1e-8
+    # two halves with carried states give the same blocks
+    if (n // bl) % 2 == 0 and block is not None:
+        h = n // 2
+        ea, sa = ofb.filter_levels(x[:h], block_len=block)
+        eb, sb = ofb.filter_levels(x[h:], block_len=block, states=sa)
+        ee = np.concatenate([ea, eb])
+        assert close(ee)
+    with pytest.raises(pfb.PfbError):
+        ofb.filter_levels(x[: n - 8], block_len=block)                   # not a multiple of the block length
+
+
+def test_bank_levels_f32(pfb, oracle):
+    import pyfilterbank_b200.sosfiltering as sf
+    rng = np.random.default_rng(9)
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000)
+    B = ofb.num_bands
+    sos = np.ascontiguousarray(ofb.sosmat.T).reshape(B, 4, 6)
+    C, n, bl = 4, 64000, 6400
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    yd, _ = oracle.sos_bank(x.astype(np.float64), sos)
+    e0 = (yd.reshape(C, B, n // bl, bl) ** 2).sum(axis=3)
+    e, _ = sf.bank_levels(sf.get_bank(sos), torch.from_numpy(x).cuda(), bl, arith64=True)
+    assert np.max(np.abs(e.cpu().numpy() - e0) / e0) <= 1e-5
+    e, _ = sf.bank_levels(sf.get_bank(sos), torch.from_numpy(x).cuda(), bl)
+    rel = np.abs(e.cpu().numpy() - e0) / e0
+    assert np.max(rel[:, 12:]) <= 1e-3, np.max(rel[:, 12:])             # float32 arithmetic: bands above ~200 Hz
