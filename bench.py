@@ -287,8 +287,9 @@ def main():
     # timed steps.  `step_frac` is the same bytes over the WHOLE step (pre-pass + carry + output pass).
     alg_bytes = C * n * esz * (B + 1)
     peak, peak_src = peaks()
-    tma = info["aligned"] == 2
-    kname = ("sos_tma_kernel<PASS_B> (output pass)" if tma else
+    tma = info["aligned"] in (2, 3)
+    kname = ("sos_tma_wide_kernel (output pass, 512-byte fragments)" if info["aligned"] == 3 else
+             "sos_tma_kernel<PASS=1> (output pass)" if tma else
              "sos_scan_kernel" if info["mode"] == 2 else "sos_seq_kernel")
     kms = kt["output"] if kt["calls"] else ms_per_step
     achieved = alg_bytes / (kms * 1e-3) / 1e9

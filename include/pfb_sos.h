@@ -118,7 +118,8 @@ typedef struct pfb_launch_info {
     int warps_per_cascade;
     int64_t chunk;        /* samples per time chunk (scan mode), n in seq mode */
     int64_t warm_total;   /* sum over cascades of pre-pass samples per chunk (scan mode) */
-    int aligned;          /* 16-byte vector path taken */
+    int aligned;          /* 0 / 1: cp.async kernels without / with 16-byte vectors; 2: TMA kernels; 3: TMA kernels
+                             with the 512-byte-fragment output pass */
 } pfb_launch_info;
 PFB_API int pfb_bank_last_launch(const pfb_bank *bank, pfb_launch_info *info);
 

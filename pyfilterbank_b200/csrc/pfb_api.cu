@@ -433,8 +433,8 @@ bool pfb::make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J
 // ------------------------------------------------------------------------------------------------
 // TMA path helpers (pfb_tma.cuh): band grouping, tile-shape cost model, one launch set.
 // ------------------------------------------------------------------------------------------------
-static void tma_bands(const pfb_bank *b, int *nb, int *G) {
-    int nbmax = env_int("PFB_TMA_NB", pfb::kTmaSmallBands);
+static void tma_bands(const pfb_bank *b, int *nb, int *G, bool wide = false) {
+    int nbmax = env_int("PFB_TMA_NB", wide ? pfb::kTmaMaxBands : pfb::kTmaSmallBands);
     nbmax = std::max(1, std::min(nbmax, pfb::kTmaMaxBands));
     const int G0 = (b->B + nbmax - 1) / nbmax;
     *nb = (b->B + G0 - 1) / G0;
@@ -444,7 +444,7 @@ static void tma_bands(const pfb_bank *b, int *nb, int *G) {
 // Tile shape: J chunks per cascade, a tile's 32 rows = JR chunks x CH channels.  Candidates: J = 1, 2, .. 16
 // (JR = J, CH = 32 / J) and J = 32 g (JR = 32, CH = 1), at most jmax.  Cost model: output pass / wave efficiency
 // of its grid, plus the pre-pass share estimated from the bands' decay lengths.
-static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int G, long long jmax) {
+static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int G, long long jmax, bool wide = false) {
     int J = env_int("PFB_TMA_J", 0);
     if (env_int("PFB_TMA_GROUPS", 0) > 0) J = 32 * env_int("PFB_TMA_GROUPS", 0);
     if (J > 0 && J <= jmax) return J;
@@ -454,7 +454,7 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
         for (int r = 0; r < b->B; ++r)
             b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20, arith64 ? 1e-11 : 1e-8);
     }
-    const double slots = 2.0 * b->sm_count;
+    const double slots = (wide ? 1.0 : 2.0) * b->sm_count;   // resident output-pass CTAs
     double best = 1e300;
     for (int cand = 0; cand < 13; ++cand) {
         const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
@@ -479,7 +479,7 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
 // One (pre-pass, carry, output | levels) launch set over J chunks of Lt samples.  Caller holds b->mu.
 static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long long ldx, void *y, long long ldy, void *states,
                    long long Lt, int J, int C, int nb, int G, cudaStream_t stream, double *levels, long long lev_ld,
-                   long long lev_off, int ut, bool may_time) {
+                   long long lev_off, int ut, bool may_time, bool wide = false) {
     const int arith = arith64 ? PFB_F64 : PFB_F32;
     const int tt = 2 * pfb::kRowBytes / (dtype == PFB_F64 ? 8 : 4);
     const int JR = std::min(J, 32), CH = 32 / JR;
@@ -520,6 +520,7 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     tp.Ktot = b->K, tp.k0 = 0;
     tp.nb_a = nb;
     tp.levels = levels, tp.lev_ld = lev_ld, tp.lev_off = lev_off, tp.ut = ut;
+    tp.wide = wide ? 1 : 0;
     if (tab) {
         tp.P = tab->P[0];
         tp.warm = tab->warm[0];
@@ -553,7 +554,7 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     b->last.warps_per_cascade = J / JR;
     b->last.chunk = Lt;
     b->last.warm_total = tab ? tab->warm_total * C : 0;
-    b->last.aligned = 2;   // 2 = TMA path
+    b->last.aligned = wide ? 3 : 2;   // 2 = TMA path, 3 = TMA path with the wide (512-byte fragment) output pass
     return PFB_OK;
 }
 
@@ -747,15 +748,34 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     long long L = n;
     const Tables *tab = nullptr;
     if (mode == PFB_MODE_SCAN && tma_ok) {
+        // Output-pass variant with 512-byte row fragments (sos_tma_wide_kernel: one CTA of up to 11 band warps per
+        // SM, 16 KB output tiles).  HBM takes 512-byte fragments ~8 % faster than 256-byte ones
+        // (profiles/r01_ubench_tma_store_rows.txt); measured on cfg 2: 12.45 -> 12.0 ms per step.  Used for float64
+        // signals of few-channel banks (chunked regime) with enough bands to fill a CTA; PFB_TMA_WIDE=0/1 overrides.
         int nb, G;
-        tma_bands(b, &nb, &G);
-        const int J = tma_pick_J(b, n, C, tt, arith64, G, 1 << 30);
+        tma_bands(b, &nb, &G, false);
+        int J = tma_pick_J(b, n, C, tt, arith64, G, 1 << 30, false);
+        bool wide = dtype == PFB_F64 && b->K <= 4 && b->B >= 9 && J >= 32;
+        wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
+        const int ttb = wide ? 2 * tt : tt;
+        if (wide) {
+            tma_bands(b, &nb, &G, true);
+            // the bandwidth-bound wide kernel is insensitive to wave quantisation (late CTAs run faster), so
+            // take the fewest chunks that still give every SM two CTAs: less pre-pass work
+            if (env_int("PFB_TMA_J", 0) <= 0 && env_int("PFB_TMA_GROUPS", 0) <= 0) {
+                J = 32;
+                while ((long long)C * G * (J / 32) < 2LL * b->sm_count && J < 256) J += 32;
+                while (J > 32 && n / J / ttb * ttb < 64LL * ttb) J -= 32;
+            } else {
+                J = tma_pick_J(b, n, C, ttb, arith64, G, 1 << 30, true);
+            }
+        }
         const int JR = std::min(J, 32);
         if (J <= 0 || J % JR != 0 || 32 % JR != 0) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad chunk count %d", J);
-        const long long Lt = n / J / tt * tt;
-        if (Lt >= 4LL * tt && Lt < 0x7fffffffLL) {
+        const long long Lt = n / J / ttb * ttb;
+        if (Lt >= 4LL * ttb && Lt < 0x7fffffffLL) {
             const long long n_main = Lt * J;
-            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true);
+            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true, wide);
             if (rc) return rc;
             pfb_launch_info main_info = b->last;
             if (n_main < n) {        // the ragged end continues from the carried states

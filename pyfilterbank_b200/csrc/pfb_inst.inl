@@ -112,8 +112,17 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             *launches += 1;
         }
         if (ev) cudaEventRecord(ev[2], s);
-        if (p.levels) kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap);   // energies instead of band signals
-        else kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+        if (p.levels) {
+            kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap);   // energies instead of band signals
+        } else if (p.wide) {
+            auto kern_w = sos_tma_wide_kernel<PFB_T, PFB_A, K, SCALED>;
+            const int smem_w = (2 + p.nb) * 4 * kTileBytes + 2 * 2 * 8;
+            e = cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w);
+            if (e != cudaSuccess) return (int)e;
+            kern_w<<<grid, threads, smem_w, s>>>(p, tab, xmap, ymap);
+        } else {
+            kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+        }
         if (ev) cudaEventRecord(ev[3], s);
         *launches += 1;
     }

@@ -56,6 +56,7 @@ struct TmaParams {
     double *levels;
     long long lev_ld, lev_off;
     int ut;
+    int wide;             // output pass with 512-byte fragments (sos_tma_wide_kernel); L is then a multiple of 4 half rows
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -157,15 +158,17 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
 // Tile row r <-> chunk JR * w + r % JR of channel CH * cb + r / JR.
 // PASS 0: pre-pass, writes zero-state chunk end states to zs; 1: output pass from zs; 2: like 1 but the band
 // signals are reduced to energies per time unit instead of being stored (band-level epilogue).
-template <typename T, typename A, int K, int PASS, bool SCALED>
+// NH: 128-byte half rows per tile step (2: 256-byte row fragments; 4: 512-byte fragments, which HBM writes ~8 %
+// faster but which need 16 KB output tiles per band warp); NS: input ring stages.
+template <typename T, typename A, int K, int PASS, bool SCALED, int NH = 2, int NS = kTmaStages>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
                                         const CUtensorMap &ymap, char *smem, int cta, int ch0) {
     constexpr bool PASS_B = PASS != 0;
     constexpr bool STORE_Y = PASS == 1;
     constexpr int TLEN = kRowBytes / (int)sizeof(T);      // samples per 128-byte half row
-    constexpr int TT = 2 * TLEN;                          // samples per tile step (256-byte rows)
+    constexpr int TT = NH * TLEN;                         // samples per tile step (NH * 128-byte rows)
     constexpr int S = 2 * K;
-    constexpr unsigned kStageBytes = 2 * kTileBytes;
+    constexpr unsigned kStageBytes = NH * kTileBytes;
     const int lane = threadIdx.x & 31, key = lane & 7;
     // warp index through a warp reduction: the result lives in a uniform register, so everything
     // indexed by it (the band's coefficients) can stay in uniform registers -- DFMA R, R, UR, R reads
@@ -179,13 +182,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     const int nb_here = min(nbw, p.B - b0);
 
     char *xs = smem;                                          // [stages][2][tile]
-    char *ys = smem + kTmaStages * kStageBytes;               // [nb][2][tile], output pass only
+    char *ys = smem + NS * kStageBytes;               // [nb][2][tile], output pass only
     uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb : 0) * kStageBytes);
-    uint64_t *empty = full + kTmaStages;
+    uint64_t *empty = full + NS;
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kTmaStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], nb_here);
         }
@@ -209,13 +212,14 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         if (lane == 0) {
             for (long long t = t_first; t < nt; ++t) {
                 const long long it = t - t_first;
-                const int s = (int)(it % kTmaStages);
-                const unsigned ph = (unsigned)((it / kTmaStages) & 1);
+                const int s = (int)(it % NS);
+                const unsigned ph = (unsigned)((it / NS) & 1);
                 mbar_wait(&empty[s], ph ^ 1u);
                 mbar_expect_tx(&full[s], kStageBytes);
                 char *dst = xs + s * kStageBytes;
-                tma_load_3d(dst, &xmap, &full[s], (int)(t * TT), p.JR * w, p.CH * cb);
-                tma_load_3d(dst + kTileBytes, &xmap, &full[s], (int)(t * TT + TLEN), p.JR * w, p.CH * cb);
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                    tma_load_3d(dst + h * kTileBytes, &xmap, &full[s], (int)(t * TT + h * TLEN), p.JR * w, p.CH * cb);
             }
         }
         return;
@@ -267,13 +271,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         int tcount = 0;
         double *lev = p.levels + (size_t)q * p.lev_ld + p.lev_off + (long long)j * (nt / p.ut);
         for (long long t = 0; t < nt; ++t) {
-            const int s = (int)(t % kTmaStages);
-            const unsigned ph = (unsigned)((t / kTmaStages) & 1);
+            const int s = (int)(t % NS);
+            const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait(&full[s], ph);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             A acc = A(0);
-            filter_half<T, A, K, 2, SCALED>(xrow, nullptr, key, c, wst, &acc);
-            filter_half<T, A, K, 2, SCALED>(xrow + kTileBytes, nullptr, key, c, wst, &acc);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) filter_half<T, A, K, 2, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst, &acc);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             acc_unit += (double)acc;
@@ -286,8 +290,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
     } else if (PASS_B) {
         for (long long t = 0; t < nt; ++t) {
-            const int s = (int)(t % kTmaStages);
-            const unsigned ph = (unsigned)((t / kTmaStages) & 1);
+            const int s = (int)(t % NS);
+            const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait(&full[s], ph);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             // the previous tile's TMA stores must have finished reading this warp's output buffer.
@@ -296,14 +300,16 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             // arrive as two separate 128-byte bursts; see profiles/r01_ubench_tma_store_rows.txt.)
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
-            filter_half<T, A, K, 1, SCALED>(xrow, yrow, key, c, wst);
-            filter_half<T, A, K, 1, SCALED>(xrow + kTileBytes, yrow + kTileBytes, key, c, wst);
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+                filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + h * kTileBytes, key, c, wst);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[s]);
-                tma_store_4d(&ymap, ybuf, (int)(t * TT), p.JR * w, band, p.CH * cb);
-                tma_store_4d(&ymap, ybuf + kTileBytes, (int)(t * TT + TLEN), p.JR * w, band, p.CH * cb);
+#pragma unroll
+                for (int h = 0; h < NH; ++h)
+                    tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
                 bulk_commit();
             }
         }
@@ -312,17 +318,17 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         long long t = t_first;
         for (; t < t_mine; ++t) {
             const long long it = t - t_first;
-            const int s = (int)(it % kTmaStages);
-            mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+            const int s = (int)(it % NS);
+            mbar_wait(&full[s], (unsigned)((it / NS) & 1));
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         for (; t < nt; ++t) {
             const long long it = t - t_first;
-            const int s = (int)(it % kTmaStages);
-            mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+            const int s = (int)(it % NS);
+            mbar_wait(&full[s], (unsigned)((it / NS) & 1));
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            filter_half<T, A, K, 0, SCALED>(xrow, nullptr, key, c, wst);
-            filter_half<T, A, K, 0, SCALED>(xrow + kTileBytes, nullptr, key, c, wst);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) filter_half<T, A, K, 0, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
@@ -568,6 +574,16 @@ bool make_y_map(CUtensorMap *map, int dtype, void *base, long long L, int J, int
 
 // ev: null, or 4 events recorded before the pre-pass and after each of the three kernels
 // phases: 1 = pre-pass, 2 = carry + output pass, 3 = all (on stream s)
+// Output pass with 512-byte row fragments: up to 11 band warps + producer, 16 KB output tile per band warp,
+// two 16 KB input stages, one CTA per SM.
+template <typename T, typename A, int K, bool SCALED>
+__global__ void __launch_bounds__((kTmaMaxBands + 1) * 32, 1)
+sos_tma_wide_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
+                    const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+    extern __shared__ __align__(1024) char smem[];
+    tma_cta<T, A, K, 1, SCALED, 4, 2>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
+}
+
 int launch_tma_dd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
                   cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
 int launch_tma_ff(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,

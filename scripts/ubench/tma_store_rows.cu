@@ -93,10 +93,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int main() {
+int sweep_L(EncodeTiledFn enc);
+
+int main(int argc, char **argv) {
     void *f = nullptr; cudaDriverEntryPointQueryResult qr;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr);
     EncodeTiledFn enc = (EncodeTiledFn)f;
+    if (argc > 1) return sweep_L(enc);
     const int Q = 2112;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int groups : {2, 6}) {
@@ -165,6 +168,36 @@ int main() {
         }
         printf("cudaMemcpy D2D (read+write bytes): %7.3f ms  %.0f GB/s\n", best, bytes / (best * 1e-3) / 1e9);
         cudaFree(y);
+    }
+    return 0;
+}
+
+// chunk-length sensitivity of the 256-byte-fragment store pattern: J = 256 chunks, row stride = L doubles
+int sweep_L(EncodeTiledFn enc) {
+    const int Q = 2112, J = 256, groups = 8;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const long long Lmax = 12544;
+    double *y; const size_t cap = (size_t)Q * Lmax * J * 8;
+    if (cudaMalloc(&y, cap) != cudaSuccess) { printf("alloc failed\n"); return 1; }
+    for (long long L : {11232LL, 11264LL, 11200LL, 11136LL, 10240LL, 12288LL, 8192LL, 11232LL + 32, 11232LL - 32, 9984LL, 12000LL, 12544LL, 4096LL, 5632LL}) {
+        const long long n = L * J;
+        const size_t bytes = (size_t)Q * n * 8;
+        CUtensorMap map;
+        cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)J, (cuuint64_t)Q};
+        cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)n * 8};
+        cuuint32_t box[3] = {16, 32, 1}, estr[3] = {1, 1, 1};
+        if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
+        const int smem = 8 * 2 * 4096;
+        cudaFuncSetAttribute(tma_wr<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        float best = 1e9;
+        for (int it = 0; it < 3; ++it) {
+            cudaEventRecord(e0);
+            tma_wr<2><<<Q / 8 * groups, 256, smem>>>(map, L, groups, 1);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        printf("J=256 256-B fragments, chunk length L=%6lld (row stride %8lld B): %7.3f ms  %.0f GB/s\n", L, L * 8, best, bytes / (best * 1e-3) / 1e9);
     }
     return 0;
 }

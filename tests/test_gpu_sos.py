@@ -235,7 +235,7 @@ def test_tma_path_parity(pfb, oracle, scaled, hform, monkeypatch):
     bank = pfb.Bank(sos)                            # fresh bank: tables built under the env setting
     xt = torch.from_numpy(x).cuda()
     y1, s1 = pfb.bank_filter(bank, xt, torch.from_numpy(st0.copy()).cuda(), mode="scan")
-    assert bank.last_launch()["aligned"] == 2       # the TMA path ran
+    assert bank.last_launch()["aligned"] in (2, 3)  # the TMA path ran
     y1, s1 = y1.cpu().numpy(), s1.cpu().numpy()
     worst = max(rel_l2(y1[:, b], y0[:, b]) for b in range(B))
     assert worst <= TOL64, worst
@@ -260,7 +260,7 @@ def test_tma_path_f32(pfb, oracle):
     bank = pfb.Bank(sos)
     xt = torch.from_numpy(x).cuda()
     y1, _ = pfb.bank_filter(bank, xt, mode="scan", arith64=True)
-    assert bank.last_launch()["aligned"] == 2
+    assert bank.last_launch()["aligned"] in (2, 3)
     y1 = y1.cpu().numpy()
     for b in range(B):
         assert rel_l2(y1[:, b], yd[:, b]) <= 1e-6, b
@@ -289,7 +289,7 @@ def test_tma_tile_shapes(pfb, oracle, J, monkeypatch):
         y0, s0 = oracle.sos_bank(x, sos, st0)
         y1, s1 = pfb.bank_filter(bank, torch.from_numpy(x).cuda(), torch.from_numpy(st0.copy()).cuda())
         info = bank.last_launch()
-        assert info["aligned"] == 2 and info["mode"] == 2, info
+        assert info["aligned"] in (2, 3) and info["mode"] == 2, info
         y1, s1 = y1.cpu().numpy(), s1.cpu().numpy()
         worst = max(rel_l2(y1[:, b], y0[:, b]) for b in range(B))
         assert worst <= TOL64, (C, n, worst)
