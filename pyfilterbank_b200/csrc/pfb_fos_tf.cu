@@ -140,8 +140,10 @@ __device__ __forceinline__ double tf_step(double xi, const double (&b)[8], const
     return yi;
 }
 
-// One lane per row, one warp per CTA (the recurrence is latency bound: 3 dependent FP64 operations per sample,
-// so rows are spread over as many SM sub-partitions as possible).  NZ = taps - 1 delay values.
+// One lane per row, one warp per CTA.  Measured (scripts/tf_time.py): a warp needs ~94 clocks per sample for the
+// 25 separately rounded FP64 operations of the 7-tap filter, and two rows per lane take exactly twice as long, so
+// the limit is the single-warp FP64 issue rate, not the dependent chain; rows are therefore spread over as many SM
+// sub-partitions as possible (one warp each).  NZ = taps - 1 delay values.
 template <int NZ, bool ALIGNED, int kTfStages>
 __global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfParams p) {
     extern __shared__ __align__(128) char smem[];
