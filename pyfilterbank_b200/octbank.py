@@ -260,9 +260,21 @@ class FractionalOctaveFilterbank:
         rows = sig.reshape(n, -1).t().contiguous()                          # (C, N)
         if weighting_states is not None and not isinstance(weighting_states, torch.Tensor):
             weighting_states = torch.from_numpy(np.array(weighting_states, dtype=np.float64)).to(rows.device)
-        w, wst = _spl.tf_filter(b, a, rows, None if weighting_states is None else weighting_states.clone())
-        y, st = _sf.sosfilter_double_mimo_c(w.t(), self.sosmat, states, mode="seq" if self._exact else "auto",
-                                            exact=self._exact)
+        wst = None if weighting_states is None else weighting_states.clone()
+        C, B, K = rows.shape[0], self.num_bands, self.order
+        bank = _sf.get_bank(np.ascontiguousarray(self.sosmat.T).reshape(B, K, 6))
+        if states is None:
+            st = torch.zeros((C, B, K, 2), dtype=torch.float64, device=rows.device)
+        else:
+            st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.array(states, dtype=np.float64).flatten('F'))
+            st = st.to(device=rows.device, dtype=torch.float64).reshape(C, B, K, 2).clone()
+        mode = "seq" if self._exact else "auto"
+        # (Running the weighting in time blocks on a side stream, one block ahead of the bank, was measured: no gain --
+        # the chunked bank loses on short blocks what the overlap wins; the weighting itself is bound by the FP64
+        # issue rate of one warp per 32 channels, ~94 clocks per sample, whatever the channel count.)
+        w, wst = _spl.tf_filter(b, a, rows, wst)
+        yb, st = _sf.bank_filter(bank, w, st, mode=mode, exact=self._exact)
+        y, st = yb.permute(2, 1, 0), st.reshape(-1)
         if on_device:
             return y, st, wst
         return y.cpu().numpy() if isinstance(y, torch.Tensor) else y, \

@@ -63,24 +63,27 @@ _weighting_coeff_design_funsd = {'A': a_weighting_coeffs_design, 'B': b_weightin
                                  'C': c_weighting_coeffs_design}
 
 
-def tf_filter(b, a, x, zi=None):
-    """lfilter(b, a, x) along the last axis of a CUDA float64 tensor (rows contiguous); returns
-    (y, zf) with zf (rows, ntaps-1) the final delay values (scipy's zi convention)."""
+def tf_filter(b, a, x, zi=None, out=None):
+    """lfilter(b, a, x) along the last axis of a CUDA float64 tensor; returns (y, zf) with zf
+    (rows, ntaps-1) the final delay values (scipy's zi convention, updated in place when `zi` is given).
+    A 2-D x may be a time slice of a larger tensor (row stride > length); `out` likewise."""
     b = np.ascontiguousarray(b, dtype=np.float64)
     a = np.ascontiguousarray(a, dtype=np.float64)
     shape = x.shape
     n = shape[-1]
-    x2 = x.reshape(-1, n).contiguous()
+    x2 = x if (x.dim() == 2 and x.stride(1) == 1) else x.reshape(-1, n).contiguous()
     R = x2.shape[0]
     nz = max(len(b), len(a)) - 1
     z = torch.zeros((R, max(nz, 1)), dtype=torch.float64, device=x.device) if zi is None else zi
-    y = torch.empty_like(x2)
+    y = torch.empty((R, n), dtype=torch.float64, device=x.device) if out is None else out
     if n > 0:
+        ldx = x2.stride(0) if R > 1 else max(n, 1)
+        ldy = y.stride(0) if R > 1 else max(n, 1)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().pfb_tf_filter_f64(x2.data_ptr(), n, y.data_ptr(), n, b.ctypes.data, len(b),
+            _lib.check(_lib.lib().pfb_tf_filter_f64(x2.data_ptr(), ldx, y.data_ptr(), ldy, b.ctypes.data, len(b),
                                                      a.ctypes.data, len(a), z.data_ptr(), n, R,
                                                      torch.cuda.current_stream().cuda_stream))
-    return y.reshape(shape), z
+    return (y.reshape(shape) if out is None else y), z
 
 
 def weight_signal(data, sample_rate=44100, weighting='A'):
