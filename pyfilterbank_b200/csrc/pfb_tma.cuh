@@ -384,11 +384,13 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
     constexpr unsigned kStageBytes = 2 * kTileBytes;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // Band groups outermost, lowest bands first: their windows are the longest (a whole chunk), so the heavy CTAs
+    // start first and the short high-band CTAs fill the tail of the grid.
     const int cta = blockIdx.x;
     const int w = cta % p.NW;
     const int cg = cta / p.NW;
     const int nbw = p.nb_a, G = p.G_a;
-    const int g = cg % G, cb = cg / G;
+    const int cb = cg % p.CB, g = cg / p.CB;
     const int b0 = g * nbw;
     const int nb_here = min(nbw, p.B - b0);
 
