@@ -20,9 +20,9 @@ if [ -z "$SKIP_NCU" ]; then
       python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu list rc=$?"
   # full capture of the pre-pass and output kernels on a quarter-length signal (same grid shape per chunk group)
   DT=f64 C=64 N=${NCU_N:-1440000} IT=2 timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:"sos_tma_kernel|sos_carry|sos_hform" -s 3 -c 3 -f -o $O/${TAG}_full_f64 python scripts/prof_case.py > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+      -k regex:"sos_tma|sos_carry|sos_hform" -s 3 -c 3 -f -o $O/${TAG}_full_f64 python scripts/prof_case.py > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
   DT=f32 C=64 N=${NCU_N:-1440000} IT=2 timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:"sos_tma_kernel|sos_hform" -s 2 -c 2 -f -o $O/${TAG}_full_f32 python scripts/prof_case.py > $O/${TAG}_ncu_full32.log 2>&1; echo "ncu full32 rc=$?"
+      -k regex:"sos_tma|sos_hform" -s 2 -c 2 -f -o $O/${TAG}_full_f32 python scripts/prof_case.py > $O/${TAG}_ncu_full32.log 2>&1; echo "ncu full32 rc=$?"
 fi
 if [ -n "$RUN_UBENCH" ]; then
   for b in $RUN_UBENCH; do timeout 120 scripts/ubench/$b.bin > $O/${TAG}_ubench_$b.txt 2>&1; echo "ubench $b rc=$?"; cat $O/${TAG}_ubench_$b.txt | tail -30; done
