@@ -1054,9 +1054,12 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)   // two slots; leave most of the device to the caller
             cap_bytes = std::min<long long>(cap_bytes, (long long)((free_b + b->hy_bytes * 2) / 4));
-        if (per_channel_bytes <= cap_bytes)
-            return filter_host_by_channels(b, dtype, x, ldx, y, ldy, states, n, C, flags,
-                                           (int)std::max<long long>(1, std::min<long long>(C, cap_bytes / per_channel_bytes)));
+        if (per_channel_bytes <= cap_bytes) {
+            // at least four groups when there are that many channels, so input copy, kernels and output drain overlap
+            long long Cg = std::max<long long>(1, std::min<long long>(C, cap_bytes / per_channel_bytes));
+            Cg = std::min<long long>(Cg, std::max<long long>(1, (C + 3) / 4));
+            return filter_host_by_channels(b, dtype, x, ldx, y, ldy, states, n, C, flags, (int)Cg);
+        }
     }
     // time block: multiple of 32 elements, sized so one output block is at most ~1 GiB
     long long nb = n;
