@@ -328,13 +328,13 @@ long long fos_warm(const double *c3, int order, long long L, double tol) {
 
 }  // namespace
 
-template <int ORDER>
-static int run_fos_tma(const FosTmaParams &p, const FosCoef &tab, const TmaParams &cp, const CUtensorMap &xmap,
-                       const CUtensorMap &ymap, cudaStream_t s) {
-    auto ka = fos_tma_kernel<ORDER, false>;
-    auto kb = fos_tma_kernel<ORDER, true>;
-    const int smem_a = kFosStages * kTileBytes + 2 * kFosStages * 8;
-    const int smem_b = (kFosStages + 2 * p.nb) * kTileBytes + 2 * kFosStages * 8;
+template <int ORDER, int NX>
+static int run_fos_tma_nx(const FosTmaParams &p, const FosCoef &tab, const TmaParams &cp, const CUtensorMap &xmap,
+                          const CUtensorMap &ymap, cudaStream_t s) {
+    auto ka = fos_tma_kernel<ORDER, false, NX>;
+    auto kb = fos_tma_kernel<ORDER, true, NX>;
+    const int smem_a = kFosStages * NX * kTileBytes + 2 * kFosStages * 8;
+    const int smem_b = (kFosStages * NX + 2 * NX * p.nb) * kTileBytes + 2 * kFosStages * 8;
     cudaError_t e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     if (e != cudaSuccess) return (int)e;
@@ -349,6 +349,11 @@ static int run_fos_tma(const FosTmaParams &p, const FosCoef &tab, const TmaParam
     kb<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
     return (int)cudaGetLastError();
 }
+template <int ORDER>
+static int run_fos_tma(const FosTmaParams &p, const FosCoef &tab, const TmaParams &cp, const CUtensorMap &xmap,
+                       const CUtensorMap &ymap, cudaStream_t s, bool wide) {
+    return wide ? run_fos_tma_nx<ORDER, 2>(p, tab, cp, xmap, ymap, s) : run_fos_tma_nx<ORDER, 1>(p, tab, cp, xmap, ymap, s);
+}
 
 // returns 0 on success, a cudaError_t otherwise; *n_done = samples filtered (0 when the shapes do not fit this
 // path; a ragged end [n_done, n) is left to the caller, states carried)
@@ -360,7 +365,12 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     int sm_count = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    const int G0 = (B + kFosMaxBands - 1) / kFosMaxBands;
+    // wide variant (512-byte output fragments, <= 11 band warps, one CTA per SM) for banks with enough bands
+    bool wide = B >= 9 && order <= 6;
+    if (const char *v = getenv("PFB_FOS_WIDE")) wide = atoi(v) != 0;
+    const int nbmax = wide ? kFosWideBands : kFosMaxBands;
+    const int tt = wide ? 32 : 16;
+    const int G0 = (B + nbmax - 1) / nbmax;
     const int nb = (B + G0 - 1) / G0, G = (B + nb - 1) / nb;
     // chunks per signal: fill the machine (2 CTAs per SM), prefer few chunks (the pre-pass is cheap: decay windows
     // of gammatone filters are a few thousand samples)
@@ -369,12 +379,12 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     int J = 0;
     if (const char *v = getenv("PFB_FOS_J")) J = atoi(v);
     if (J <= 0) {
-        const double slots = 2.0 * sm_count;
+        const double slots = (wide ? 1.0 : 2.0) * sm_count;
         double best = 1e300;
         for (int cand = 0; cand < 13; ++cand) {
             const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
             const int jr = std::min(j, 32), chn = 32 / jr;
-            if (j > 1 && n / j / 16 * 16 < 64 * 16) break;
+            if (j > 1 && n / j / tt * tt < 64 * tt) break;
             const long long cb = (C + chn - 1) / chn;
             const double waves = (double)cb * G * (j / jr) / slots;
             double eff = waves >= 1 ? waves / std::ceil(waves) : waves;
@@ -389,8 +399,8 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     }
     const int JR = std::min(J, 32), CH = 32 / JR;
     if (JR * CH != 32 || J % JR) return (int)cudaErrorInvalidValue;
-    const long long Lt = n / J / 16 * 16;
-    if (Lt < 64 || 2 * Lt >= 0x7fffffffLL) return 0;
+    const long long Lt = n / J / tt * tt;
+    if (Lt < 4 * tt || 2 * Lt >= 0x7fffffffLL) return 0;
     const long long n_main = Lt * J, Q = (long long)C * B;
     CUtensorMap xmap, ymap;
     if (!make_x_map(&xmap, PFB_F64, x, Lt, J, C, ldx, JR, CH) ||
@@ -431,13 +441,13 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     }
     int err;
     switch (order) {
-        case 1: err = run_fos_tma<1>(p, tab, cp, xmap, ymap, s); break;
-        case 2: err = run_fos_tma<2>(p, tab, cp, xmap, ymap, s); break;
-        case 3: err = run_fos_tma<3>(p, tab, cp, xmap, ymap, s); break;
-        case 4: err = run_fos_tma<4>(p, tab, cp, xmap, ymap, s); break;
-        case 5: err = run_fos_tma<5>(p, tab, cp, xmap, ymap, s); break;
-        case 6: err = run_fos_tma<6>(p, tab, cp, xmap, ymap, s); break;
-        case 8: err = run_fos_tma<8>(p, tab, cp, xmap, ymap, s); break;
+        case 1: err = run_fos_tma<1>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 2: err = run_fos_tma<2>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 3: err = run_fos_tma<3>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 4: err = run_fos_tma<4>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 5: err = run_fos_tma<5>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 6: err = run_fos_tma<6>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 8: err = run_fos_tma<8>(p, tab, cp, xmap, ymap, s, wide); break;
         default: err = (int)cudaErrorInvalidValue;
     }
     if (scratch) cudaFreeAsync(scratch, s);
