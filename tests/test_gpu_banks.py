@@ -283,3 +283,30 @@ def test_bank_levels_f32(pfb, oracle):
     e, _ = sf.bank_levels(sf.get_bank(sos), torch.from_numpy(x).cuda(), bl)
     rel = np.abs(e.cpu().numpy() - e0) / e0
     assert np.max(rel[:, 12:]) <= 1e-3, np.max(rel[:, 12:])             # float32 arithmetic: bands above ~200 Hz
+
+
+def test_gammatone_full_size_cfg4(pfb, oracle):
+    """BASELINE.json configs[3] at full size (64 ERB bands, 512 signals x 10 s @ 16 kHz, 84 GB of complex128 bands):
+    whole rows against the oracle and batch-independence (a signal's bands do not depend on its batch mates)."""
+    from pyfilterbank_b200 import gammatone as gt
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs 100 GB of free device memory")
+    gfb = pfb.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
+    C, n = 512, 160000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    x = torch.randn((C, n), generator=gen, device="cuda", dtype=torch.float64)
+    y, st = gt.fos_bank(x, gfb._coef_rows, 4)
+    assert y.shape == (C, 64, n)
+    for c in (0, 300, 511):
+        xr = x[c].cpu().numpy()
+        for i in (0, 40, 63):
+            b, a = gfb._coeffs[i]
+            y0, s0 = oracle.fosfilter(b, a, 4, xr)
+            assert rel_l2(y[c, i].cpu().numpy(), y0) <= 1e-11, (c, i)
+            assert rel_l2(st[c, i].cpu().numpy(), s0) <= 1e-10
+    ref = y[7].clone()
+    del y
+    y1, _ = gt.fos_bank(x[7:8].contiguous(), gfb._coef_rows, 4)
+    assert float((y1[0] - ref).abs().max()) <= 1e-12 * float(ref.abs().max())

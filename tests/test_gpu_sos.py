@@ -323,3 +323,51 @@ def test_bank_filter_host_streaming(pfb, oracle, block_mb, monkeypatch):
     ye = np.empty((C, B, n))
     bank.filter_host(_lib.PFB_F64, x, n, ye, n, st, n, C, _lib.flags_of("seq", exact=True))
     assert np.array_equal(ye, y0) and np.array_equal(st, s0)
+
+
+def test_full_size_cfg2_properties(pfb, oracle):
+    """BASELINE.json configs[1] at full size (64 channels x 60 s @ 48 kHz, 33 bands, float64; 48.7 GB of band
+    signals): whole rows against the oracle, and the size-independent properties block-carry == one-shot and
+    zeros -> zeros through per-(channel, band) checksums."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs 60 GB of free device memory")
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    C, n = 64, 2880000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2026)
+    x = torch.randn((C, n), generator=gen, device="cuda", dtype=torch.float64)
+    bank = pfb.Bank(sos)
+    y = torch.empty((C, B, n), device="cuda", dtype=torch.float64)
+    _, st = pfb.bank_filter(bank, x, out=y)
+    assert bank.last_launch()["aligned"] in (2, 3)
+    for c in (0, 31, 63):
+        xr = x[c:c + 1].cpu().numpy()
+        for b in (0, 16, 32):
+            y0, s0 = oracle.sos_bank(xr, sos[b:b + 1])
+            err = rel_l2(y[c, b].cpu().numpy(), y0[0, 0])
+            assert err <= TOL64, (c, b, err)
+            assert rel_l2(st[c, b].cpu().numpy(), s0[0, 0]) <= 1e-7, (c, b)
+
+    def checksums(t):
+        s1 = torch.empty((C, B), dtype=torch.float64, device="cuda")
+        s2 = torch.empty((C, B), dtype=torch.float64, device="cuda")
+        w = torch.linspace(0.5, 1.5, n, dtype=torch.float64, device="cuda")
+        for c in range(C):                       # per channel: bounded temporaries
+            s1[c] = (t[c] * w).sum(dim=1)
+            s2[c] = (t[c] * t[c]).sum(dim=1)
+        return s1.cpu().numpy(), s2.cpu().numpy()
+    a1, a2 = checksums(y)
+    st_one = st.clone()
+    # two blocks with carried states into the same buffer
+    cut = 1310720 + 64
+    _, stb = pfb.bank_filter(bank, x[:, :cut], out=y[:, :, :cut])
+    _, stb = pfb.bank_filter(bank, x[:, cut:], stb, out=y[:, :, cut:])
+    b1, b2 = checksums(y)
+    assert np.max(np.abs(b2 - a2) / a2) <= 1e-9
+    assert np.max(np.abs(b1 - a1) / np.sqrt(a2 * n)) <= 1e-9
+    assert rel_l2(stb.cpu().numpy(), st_one.cpu().numpy()) <= 1e-7
+    x.zero_()
+    _, stz = pfb.bank_filter(bank, x, out=y)
+    assert float(y.abs().max()) == 0.0 and float(stz.abs().max()) == 0.0
