@@ -20,7 +20,6 @@ constexpr int kFosWideBands = 11;                // wide variant: 512-byte outpu
 
 struct FosTmaParams {
     void *zs;             // [Q][J][2*ORDER]
-    const double *states_in;   // unused (states are read / written through `states`)
     double *states;       // [Q][ORDER][2]
     const int *warm;      // [B] pre-pass samples per chunk
     long long L;

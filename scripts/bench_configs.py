@@ -75,6 +75,29 @@ def cfg3_dec(C=1024, seconds=4):
            {"band_equivalents": load, "bands": ofb.num_bands})
 
 
+def cfg3_stream(C=1024, block_s=3, blocks=10):
+    """configs[2] at its full duration: 1024 channels x 30 s streamed as 10 blocks of 3 s with carried states
+    (anti-alias, decimator phase and band states); the 0.43 TB of decimated bands are produced and dropped."""
+    ofb = p.FractionalOctaveFilterbank(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51)
+    n = 48000 * block_s
+    x = (torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1).t()
+    load = float((1.0 / ofb.decimation_factors).sum())
+    st = None
+    for _ in range(2):
+        _, st = ofb.filter_decimated(x, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(blocks):
+        out, st = ofb.filter_decimated(x, st)
+        del out
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s streamed in %d-s blocks with carried states" % (C, block_s * blocks, block_s),
+           ms, C * ofb.num_bands * n * blocks, C * n * blocks * 8 * (1 + load), {"band_equivalents": load})
+
+
 def cfg4(C=512, seconds=10):
     gfb = gt.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
     B, n = len(gfb.centerfrequencies), 16000 * seconds
@@ -105,7 +128,7 @@ def cfg5(C=1024, seconds=5, dtype=torch.float64):
            C * B * n, C * n * (8 + esz * B), {"weighting_kernel_ms": msw, "launch": bank.last_launch()})
 
 
-CASES = {"cfg1": cfg1, "cfg3_full": cfg3_full, "cfg3_dec": cfg3_dec, "cfg4": cfg4, "cfg5": cfg5,
+CASES = {"cfg1": cfg1, "cfg3_full": cfg3_full, "cfg3_dec": cfg3_dec, "cfg3_stream": cfg3_stream, "cfg4": cfg4, "cfg5": cfg5,
          "cfg5_f32": lambda: cfg5(dtype=torch.float32)}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES)):
