@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=int, default=SECONDS)
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
+    ap.add_argument("--signal", default="noise", choices=["noise", "sweep"],
+                    help="synthetic input: white noise (sigma 0.1) or a log-sine sweep 10 Hz -> 0.45 fs, amplitude 0.5, "
+                         "per-channel phase offset (SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -238,7 +241,16 @@ def main():
     bank = pfb.Bank(sos)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    x = torch.randn((C, n), generator=gen, device=dev, dtype=tdt) * 0.1
+    if args.signal == "noise":
+        x = torch.randn((C, n), generator=gen, device=dev, dtype=tdt) * 0.1
+    else:   # log-sine sweep, the same on every channel up to a phase offset 2 pi c / C_total
+        t = torch.arange(n, device=dev, dtype=torch.float64) / FS
+        f0, f1, T = 10.0, 0.45 * FS, n / FS
+        k = (f1 / f0) ** (1.0 / T)
+        phase = 2 * np.pi * f0 * (k ** t - 1.0) / np.log(k)
+        ch = (torch.arange(C, device=dev, dtype=torch.float64) + rank * C) / (world * C)
+        x = (0.5 * torch.sin(phase[None, :] + 2 * np.pi * ch[:, None])).to(tdt)
+        del t, phase
     y = torch.empty((C, B, n), device=dev, dtype=tdt)
     states = torch.zeros((C, B, K, 2), device=dev, dtype=tdt)
 
@@ -376,7 +388,8 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                          "data": "synthetic (%s)" % ("white noise" if args.signal == "noise" else "log-sine sweep"),
                           "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                           "gpu_launches": int(info["kernels"]) * args.steps, "clocks": clocks,
                           "launch": info, "gather": gather}))
