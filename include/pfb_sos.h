@@ -143,6 +143,14 @@ PFB_API int pfb_bank_timing_end(pfb_bank *bank, double *ms, int *calls);
 PFB_API int pfb_fos_bank_c128(const double *x, int64_t ldx, double *y, int64_t ldy, const double *coef, int B,
                               int order, double *states, int64_t n, int C, void *stream);
 
+/* GammatoneFilterbank.synthesize / delay (gammatone.py:323-340), fused: out[c][t] = sum over bands (ascending) of the
+ * band's gain-weighted real part delayed by its delay (first samples from delay_memory, which is then refilled with
+ * the block's last samples); a band with delay 0 contributes Re(band) * phase factor instead.
+ *   bands [C][B][ldb] complex128; out [C][ldo] complex128; delay_memory [C][B][dmax] real in/out;
+ *   par HOST [B][4] = gain, delay_samples, Re phase factor, Im phase factor; every delay <= min(dmax, n). */
+PFB_API int pfb_gt_synthesize_c128(const double *bands, int64_t ldb, double *out, int64_t ldo, double *delay_memory,
+                                   const double *par, int B, int dmax, int64_t n, int C, void *stream);
+
 /* splweighting.weight_signal (splweighting.py:79-80): y = lfilter(b, a, x) per row, direct form II
  * transposed in scipy's operation order; b, a HOST arrays (at most 8 taps); z [R][max(nb,na)-1] delay
  * values in/out (zeros for the reference's behaviour). */

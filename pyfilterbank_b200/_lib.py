@@ -55,6 +55,8 @@ def lib():
         L.pfb_bank_set_warm_tol.restype = ci
         L.pfb_fos_bank_c128.argtypes = [vp, i64, vp, i64, vp, ci, ci, vp, i64, ci, vp]
         L.pfb_fos_bank_c128.restype = ci
+        L.pfb_gt_synthesize_c128.argtypes = [vp, i64, vp, i64, vp, vp, ci, ci, i64, ci, vp]
+        L.pfb_gt_synthesize_c128.restype = ci
         L.pfb_tf_filter_f64.argtypes = [vp, i64, vp, i64, vp, ci, vp, ci, vp, i64, ci, vp]
         L.pfb_tf_filter_f64.restype = ci
         L.pfb_last_error.restype = ctypes.c_char_p

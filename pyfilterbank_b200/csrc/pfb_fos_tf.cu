@@ -458,6 +458,49 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
 
 }  // namespace pfb
 
+namespace pfb {
+
+// GammatoneFilterbank.synthesize / delay (pyfilterbank/gammatone.py:323-340), fused: every band's real part is
+// delayed by its own delay_samples[b] (the first samples come from the delay memory of the previous block), bands
+// with delay 0 are multiplied by their complex phase factor instead, and the bands are summed in ascending order
+// (the order of numpy's sum over axis 0).  One thread per output sample; the band reads are coalesced along time.
+//   bands [C][B][ldb] complex128, out [C][ldo] complex128 (imaginary part 0 unless a band has delay 0),
+//   mem [C][B][dmax] real in/out, par [B][4] = gain, delay, Re phase factor, Im phase factor
+__global__ void __launch_bounds__(256) gt_synth_kernel(const double2 *bands, long long ldb, double2 *out, long long ldo,
+                                                       const double *mem, const double *par, int B, int dmax, long long n,
+                                                       int C) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (t >= n) return;
+    double re = 0.0, im = 0.0;
+    const double2 *bc = bands + (size_t)c * B * ldb;
+    for (int b = 0; b < B; ++b) {
+        const double g = par[4 * b];
+        const long long d = (long long)par[4 * b + 1];
+        if (d == 0) {
+            const double v = __dmul_rn(bc[(size_t)b * ldb + t].x, g);
+            re = __dadd_rn(re, __dmul_rn(v, par[4 * b + 2]));
+            im = __dadd_rn(im, __dmul_rn(v, par[4 * b + 3]));
+        } else {
+            const double v = t < d ? mem[((size_t)c * B + b) * dmax + t] : __dmul_rn(bc[(size_t)b * ldb + t - d].x, g);
+            re = __dadd_rn(re, v);
+        }
+    }
+    out[(size_t)c * ldo + t] = make_double2(re, im);
+}
+
+// new delay memory: mem[c][b][i] = gain_b * Re band[c][b][n - d_b + i], i < d_b (after the synthesis kernel has read the old one)
+__global__ void gt_delay_memory_kernel(const double2 *bands, long long ldb, double *mem, const double *par, int B, int dmax,
+                                       long long n, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y, c = blockIdx.z;
+    const long long d = (long long)par[4 * b + 1];
+    if (i >= d || d > n) return;
+    mem[((size_t)c * B + b) * dmax + i] = __dmul_rn(bands[((size_t)c * B + b) * ldb + n - d + i].x, par[4 * b]);
+}
+
+}  // namespace pfb
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +555,29 @@ int pfb_tf_filter_f64(const double *x, int64_t ldx, double *y, int64_t ldy, cons
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (ldx * 8) % 16 == 0 && (ldy * 8) % 16 == 0;
     int err = pfb::launch_tf(p, aligned, (cudaStream_t)stream);
     if (err) return pfb_set_error(PFB_ERR_CUDA, cudaGetErrorString((cudaError_t)err));
+    return pfb_set_error(PFB_OK, "");
+}
+
+int pfb_gt_synthesize_c128(const double *bands, int64_t ldb, double *out, int64_t ldo, double *delay_memory,
+                           const double *par_host, int B, int dmax, int64_t n, int C, void *stream) {
+    if (n == 0) return pfb_set_error(PFB_OK, "");
+    if (!bands || !out || !delay_memory || !par_host || B <= 0 || C <= 0 || n < 0 || ldb < n || ldo < n || dmax < 1)
+        return pfb_set_error(PFB_ERR_INVALID, "pfb_gt_synthesize_c128: bad argument");
+    for (int b = 0; b < B; ++b)
+        if (par_host[4 * b + 1] < 0 || par_host[4 * b + 1] > dmax || par_host[4 * b + 1] > (double)n)
+            return pfb_set_error(PFB_ERR_INVALID, "pfb_gt_synthesize_c128: every delay must be <= dmax and <= n");
+    cudaStream_t s = (cudaStream_t)stream;
+    double *dpar = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&dpar, (size_t)B * 4 * sizeof(double), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpar, par_host, (size_t)B * 4 * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return pfb_set_error(PFB_ERR_CUDA, cudaGetErrorString(e));
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)C);
+    pfb::gt_synth_kernel<<<grid, 256, 0, s>>>((const double2 *)bands, ldb, (double2 *)out, ldo, delay_memory, dpar, B, dmax, n, C);
+    dim3 gridm((unsigned)((dmax + 127) / 128), (unsigned)B, (unsigned)C);
+    pfb::gt_delay_memory_kernel<<<gridm, 128, 0, s>>>((const double2 *)bands, ldb, delay_memory, dpar, B, dmax, n, C);
+    e = cudaGetLastError();
+    cudaFreeAsync(dpar, s);
+    if (e != cudaSuccess) return pfb_set_error(PFB_ERR_CUDA, cudaGetErrorString(e));
     return pfb_set_error(PFB_OK, "");
 }
 

@@ -173,6 +173,75 @@ class GammatoneFilterbank:
             band = y[:, i] if batched else y[0, i]
             yield band, (st[:, i] if batched else st[0, i])
 
+    # ------------------------------------------------------------------------------------------
+    # synthesis side (gammatone.py:323-340)
+    # ------------------------------------------------------------------------------------------
+    def _synth_par(self):
+        pf = np.abs(self.slopes) * 1j / self.slopes                      # gammatone.py:328
+        self.phase_factors = pf
+        return np.ascontiguousarray(np.stack([np.asarray(self.gains, dtype=np.float64),
+                                              np.asarray(self.delay_samples, dtype=np.float64),
+                                              pf.real, pf.imag], axis=1))
+
+    def synthesize_batch(self, bands, delay_memory=None):
+        """Fused delay + weighted sum of a batch: bands (C, B, N) complex128 CUDA tensor ->
+        (out (C, N) complex128, delay_memory (C, B, Dmax) float64).  One kernel reads every band once
+        (pfb_gt_synthesize_c128); `delay_memory` carries the delayed tails between blocks."""
+        C, B, N = bands.shape
+        dmax = max(int(np.max(self.delay_samples)), 1)
+        if delay_memory is None:
+            delay_memory = torch.zeros((C, B, dmax), dtype=torch.float64, device=bands.device)
+        bands = bands.contiguous()
+        out = torch.empty((C, N), dtype=torch.complex128, device=bands.device)
+        par = self._synth_par()
+        if N > 0:
+            with torch.cuda.device(bands.device):
+                _lib.check(_lib.lib().pfb_gt_synthesize_c128(bands.data_ptr(), N, out.data_ptr(), N, delay_memory.data_ptr(),
+                                                             par.ctypes.data, B, dmax, N, C,
+                                                             torch.cuda.current_stream().cuda_stream))
+        return out, delay_memory
+
+    def synthesize(self, bands):
+        """Sum of the gain-weighted, delayed bands (gammatone.py:323-325) of ONE signal: `bands` is the
+        sequence of (N,) complex bands `analyze` yields.  `self.delay_memory` (B, Dmax) is read and updated like
+        in the reference.  Returns a real array unless a band has delay 0 (then complex, like the reference)."""
+        bands = list(bands)
+        on_device = isinstance(bands[0], torch.Tensor) and bands[0].is_cuda
+        dev = bands[0].device if on_device else _device()
+        if on_device:
+            stack = torch.stack([b.to(torch.complex128) for b in bands]).unsqueeze(0)
+        else:
+            stack = torch.from_numpy(np.stack([np.asarray(b, dtype=np.complex128) for b in bands])).to(dev).unsqueeze(0)
+        mem = torch.from_numpy(np.ascontiguousarray(self.delay_memory, dtype=np.float64)).to(dev).unsqueeze(0)
+        if mem.shape[2] == 0:
+            mem = torch.zeros((1, len(bands), 1), dtype=torch.float64, device=dev)
+        out, mem = self.synthesize_batch(stack, mem)
+        if self.delay_memory.shape[1] > 0:
+            self.delay_memory = mem[0].cpu().numpy()
+        y = out[0]
+        if not np.any(np.asarray(self.delay_samples) == 0):
+            y = y.real
+        return y if on_device else y.cpu().numpy()
+
+    def delay(self, bands):
+        """Generator of the delayed real parts (gammatone.py:327-340); updates `self.delay_memory`.  Plain
+        tensor slicing (this is glue, not a kernel: `synthesize` is the fused path)."""
+        self.phase_factors = np.abs(self.slopes) * 1j / self.slopes
+        for i, band in enumerate(bands):
+            d = int(self.delay_samples[i])
+            on_device = isinstance(band, torch.Tensor)
+            re = band.real if on_device else np.real(band)
+            if d == 0:
+                yield re * complex(self.phase_factors[i])
+            else:
+                mem = self.delay_memory[i, :d]
+                if on_device:
+                    yield torch.cat([torch.from_numpy(mem.copy()).to(band.device), re[:-d]])
+                    self.delay_memory[i, :d] = re[-d:].cpu().numpy()
+                else:
+                    yield np.concatenate((mem, re[:-d]), axis=0)
+                    self.delay_memory[i, :d] = re[-d:]
+
     def estimate_max_indices_and_slopes(self, delay_samples=None):
         if not delay_samples:
             delay_samples = int(self.samplerate / 10)
