@@ -371,3 +371,35 @@ def test_full_size_cfg2_properties(pfb, oracle):
     x.zero_()
     _, stz = pfb.bank_filter(bank, x, out=y)
     assert float(y.abs().max()) == 0.0 and float(stz.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("J", [0, 1, 4, 32, 64])
+def test_no_writes_outside_the_output_rows(pfb, J, monkeypatch):
+    """Guard bands: outputs live in a pitched buffer whose padding (and the states' surroundings) hold a sentinel;
+    every kernel family must leave them untouched (compute-sanitizer is not available on the GPU pool)."""
+    from pyfilterbank_b200 import gammatone as gt
+    if J:
+        monkeypatch.setenv("PFB_TMA_J", str(J))
+        monkeypatch.setenv("PFB_FOS_J", str(J))
+    sent = -777.25
+    rng = np.random.default_rng(J)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    bank = pfb.Bank(sos)
+    for C, n, pad in ((3, 9000, 32), (37, 4608, 64), (5, 3001, 7)):
+        for dt in (torch.float64, torch.float32):
+            x = torch.from_numpy(rng.standard_normal((C, n))).to("cuda", dt)
+            big = torch.full((C, B, n + pad), sent, dtype=dt, device="cuda")
+            stbig = torch.full((C * B * K * 2 + 64,), sent, dtype=dt, device="cuda")
+            st = stbig[32:32 + C * B * K * 2].view(C, B, K, 2)
+            st.zero_()
+            for mode in ("auto", "seq"):
+                pfb.bank_filter(bank, x, st, mode=mode, out=big[:, :, :n])
+                assert bool((big[:, :, n:] == sent).all()), (C, n, dt, mode)
+                assert bool((stbig[:32] == sent).all()) and bool((stbig[-32:] == sent).all())
+                assert bool(torch.isfinite(big[:, :, :n]).all())
+    gfb = pfb.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
+    for C, n in ((5, 8000 + 6), (2, 4099)):
+        x = torch.from_numpy(rng.standard_normal((C, n))).cuda()
+        y, _ = gt.fos_bank(x, gfb._coef_rows, 4)
+        assert bool(torch.isfinite(torch.view_as_real(y)).all())
