@@ -680,9 +680,19 @@ int pfb_bank_last_launch(const pfb_bank *b, pfb_launch_info *info) {
     return PFB_OK;
 }
 
+// pfb_bank_filter with the bank's mutex already held (the TMA path calls it again for the ragged end of a signal)
+static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
+                              int64_t n, int C, int flags, void *stream_);
+
 int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
                     int64_t n, int C, int flags, void *stream_) {
     if (!b) return fail(PFB_ERR_INVALID, "pfb_bank_filter: null bank");
+    std::lock_guard<std::mutex> lock(b->mu);
+    return bank_filter_locked(b, dtype, x, ldx, y, ldy, states, n, C, flags, stream_);
+}
+
+static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
+                              int64_t n, int C, int flags, void *stream_) {
     if (n == 0) {   // nothing to filter: states stay as they are (sosfilt.c loads and stores them unchanged)
         g_status = PFB_OK;
         return PFB_OK;
@@ -716,7 +726,6 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     if (in_place && (b->B != 1 || ldx != ldy || dec))
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: x may alias y only for single-band banks with ldx == ldy");
 
-    std::lock_guard<std::mutex> lock(b->mu);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int esz = dtype == PFB_F64 ? 8 : 4;
     const int tlen = pfb::kRowBytes / esz;
@@ -779,10 +788,8 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
             if (rc) return rc;
             pfb_launch_info main_info = b->last;
             if (n_main < n) {        // the ragged end continues from the carried states
-                b->mu.unlock();
-                rc = pfb_bank_filter(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
-                                     states, n - n_main, C, (flags & ~PFB_MODE_MASK) | 0x100 | PFB_MODE_AUTO, stream_);
-                b->mu.lock();
+                rc = bank_filter_locked(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
+                                        states, n - n_main, C, (flags & ~PFB_MODE_MASK) | 0x100 | PFB_MODE_AUTO, stream_);
                 if (rc) return rc;
                 main_info.kernels += b->last.kernels;
             }
