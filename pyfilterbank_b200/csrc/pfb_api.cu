@@ -764,7 +764,10 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         int nb, G;
         tma_bands(b, &nb, &G, false);
         int J = tma_pick_J(b, n, C, tt, arith64, G, 1 << 30, false);
-        bool wide = dtype == PFB_F64 && b->K <= 4 && b->B >= 9 && J >= 32;
+        // (few channels: the wide kernel's one CTA per SM leaves SMs idle -- measured slower below ~24 channels,
+        // scripts/wide_probe.py -- so it needs enough (channel, band group) pairs for two CTAs per SM at J <= 128)
+        const int Gw = (b->B + pfb::kTmaMaxBands - 1) / pfb::kTmaMaxBands;
+        bool wide = dtype == PFB_F64 && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
         const int ttb = wide ? 2 * tt : tt;
         if (wide) {
