@@ -168,7 +168,8 @@ class GammatoneFilterbank:
             st = torch.as_tensor(np.stack(rows).reshape(B, C, self.order)).permute(1, 0, 2).contiguous().to(dev)
         y, st = fos_bank(x, self._coef_rows, self.order, st)
         if not on_device:
-            y, st = y.cpu().numpy(), st.cpu().numpy()
+            from .sosfiltering import _to_host
+            y, st = _to_host(y), st.cpu().numpy()
         for i in range(B):
             band = y[:, i] if batched else y[0, i]
             yield band, (st[:, i] if batched else st[0, i])

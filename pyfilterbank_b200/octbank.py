@@ -277,8 +277,7 @@ class FractionalOctaveFilterbank:
         y, st = yb.permute(2, 1, 0), st.reshape(-1)
         if on_device:
             return y, st, wst
-        return y.cpu().numpy() if isinstance(y, torch.Tensor) else y, \
-            st.cpu().numpy() if isinstance(st, torch.Tensor) else st, wst.cpu().numpy()
+        return _sf._to_host(yb).transpose(2, 1, 0), st.cpu().numpy(), wst.cpu().numpy()
 
     def filter_levels(self, x, block_len=None, states=None, db=False):
         """Band energies without the band signals (opt-in; the reference's users compute
@@ -351,6 +350,6 @@ class FractionalOctaveFilterbank:
         st_rows = st_t.reshape(B, 2 * K)
         if on_device:
             return y.t(), {f: st_rows[i] for i, f in enumerate(cfs)}
-        y_data = np.ascontiguousarray(y.cpu().numpy().T)
+        y_data = _sf._to_host(y.t().contiguous())                           # (N, B) C-ordered like the reference
         st_np = st_rows.cpu().numpy()
         return y_data, {f: st_np[i].copy() for i, f in enumerate(cfs)}

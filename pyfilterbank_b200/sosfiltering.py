@@ -104,6 +104,16 @@ def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
     return out[:, :, :nblocks], states
 
 
+def _to_host(t):
+    """Device tensor -> numpy array.  Large results go through page-locked memory (PCIe DMA at full rate into the
+    array the caller receives; torch's host allocator recycles the pinned blocks of results that were dropped)."""
+    if t.numel() * t.element_size() < (8 << 20):
+        return t.cpu().numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t)
+    return host.numpy()
+
+
 def _sos_rows(sos):
     sos = np.asarray(sos)
     return np.array(sos, dtype=np.float64).reshape(-1, 6)
@@ -196,7 +206,7 @@ def sosfilter_double_mimo_c(signal, sos, states=None, *, mode="auto", exact=Fals
     st = st.reshape(-1)
     if on_device:
         return y.permute(2, 1, 0), st
-    return y.cpu().numpy().transpose(2, 1, 0), st.cpu().numpy()
+    return _to_host(y).transpose(2, 1, 0), st.cpu().numpy()
 
 
 def bilinear_sos(d, c):

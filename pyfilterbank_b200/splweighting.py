@@ -93,4 +93,5 @@ def weight_signal(data, sample_rate=44100, weighting='A'):
     if isinstance(data, torch.Tensor) and data.is_cuda:
         return tf_filter(b, a, data.to(torch.float64))[0]
     x = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(_device())
-    return tf_filter(b, a, x)[0].cpu().numpy()
+    from .sosfiltering import _to_host
+    return _to_host(tf_filter(b, a, x)[0])
