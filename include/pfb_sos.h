@@ -108,7 +108,8 @@ PFB_API int pfb_bank_filter_host(pfb_bank *bank, int dtype, const void *x, int64
 /* Time-chunked mode hands every chunk the zero-state response to the last W samples of its
  * predecessor (plus the exactly propagated older state).  W is chosen per band from the band's impulse
  * response so that the dropped tail stays below `tol` relative L2 (default 1e-11, two orders under the
- * float64 parity budget; env PFB_WARM_TOL overrides).  tol = 0 forces W = chunk length (no truncation). */
+ * float64 parity budget; float32 arithmetic uses max(tol, 1e-6), two orders under its 1e-4 budget; env
+ * PFB_WARM_TOL overrides).  tol = 0 forces W = chunk length (no truncation). */
 PFB_API int pfb_bank_set_warm_tol(pfb_bank *bank, double tol);
 
 /* Introspection used by the bench harness: what the last pfb_bank_filter on this bank launched. */

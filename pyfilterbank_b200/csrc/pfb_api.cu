@@ -278,7 +278,8 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
         b->tables.clear();
     }
     Tables t;
-    const double tol = arith == PFB_F64 ? b->warm_tol : (b->warm_tol > 0 ? std::max(b->warm_tol, 1e-8) : 0.0);
+    // float32 arithmetic: 1e-6, two orders under its 1e-4 parity budget (float64: 1e-11 under 1e-9)
+    const double tol = arith == PFB_F64 ? b->warm_tol : (b->warm_tol > 0 ? std::max(b->warm_tol, 1e-6) : 0.0);
     // rows with identical coefficients (a bank tiled per channel) share their tables
     std::map<std::string, int> first_row;
     std::vector<int> same_as(b->rows);
@@ -452,7 +453,7 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
     if (b->wproxy.empty()) {   // decay length of every band (pre-pass window if chunks were unbounded)
         b->wproxy.resize(b->B);
         for (int r = 0; r < b->B; ++r)
-            b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20, arith64 ? 1e-11 : 1e-8);
+            b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20, arith64 ? 1e-11 : 1e-6);
     }
     const double slots = (wide ? 1.0 : 2.0) * b->sm_count;   // resident output-pass CTAs
     double best = 1e300;
@@ -767,16 +768,19 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         // (few channels: the wide kernel's one CTA per SM leaves SMs idle -- measured slower below ~24 channels,
         // scripts/wide_probe.py -- so it needs enough (channel, band group) pairs for two CTAs per SM at J <= 128)
         const int Gw = (b->B + pfb::kTmaMaxBands - 1) / pfb::kTmaMaxBands;
-        bool wide = dtype == PFB_F64 && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
+        const bool same_arith = dtype == PFB_F64 || !arith64;   // float64 / float64 or float32 / float32
+        bool wide = same_arith && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
         const int ttb = wide ? 2 * tt : tt;
         if (wide) {
             tma_bands(b, &nb, &G, true);
-            // the bandwidth-bound wide kernel is insensitive to wave quantisation (late CTAs run faster), so
-            // take the fewest chunks that still give every SM two CTAs: less pre-pass work
+            // Few chunks mean little pre-pass work; the wide kernel runs one CTA per SM, so the grid is sized in
+            // CTAs per SM: two for float64 (bandwidth bound, late CTAs run faster, insensitive to the partial last
+            // round), three and a half for float32 (issue bound: the partial round costs).  Sweeps in profiles/.
             if (env_int("PFB_TMA_J", 0) <= 0 && env_int("PFB_TMA_GROUPS", 0) <= 0) {
+                const long long want = dtype == PFB_F64 ? 2LL * b->sm_count : 7LL * b->sm_count / 2;
                 J = 32;
-                while ((long long)C * G * (J / 32) < 2LL * b->sm_count && J < 256) J += 32;
+                while ((long long)C * G * (J / 32) < want && J < 256) J += 32;
                 while (J > 32 && n / J / ttb * ttb < 64LL * ttb) J -= 32;
             } else {
                 J = tma_pick_J(b, n, C, ttb, arith64, G, 1 << 30, true);

@@ -300,7 +300,9 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             // arrive as two separate 128-byte bursts; see profiles/r01_ubench_tma_store_rows.txt.)
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
-#pragma unroll
+            // float32 wide tiles: keep the four half rows a loop (fully unrolled they are ~24 KB of code per
+            // warp iteration and the kernel stalls on instruction fetch)
+#pragma unroll(sizeof(T) == 4 && NH == 4 ? 1 : NH)
             for (int h = 0; h < NH; ++h)
                 filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + h * kTileBytes, key, c, wst);
             fence_proxy_async();
