@@ -137,6 +137,24 @@ class ClockSampler:
                 "samples": len(inside), "source": self.mode}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Several ranks share one host: run this rank (and first-touch its pinned buffers) on the CPU cores NVML reports
+    as local to its GPU, so the host side of the PCIe copies stays on the GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
     """Reference C (`sosfilter_double`, sosfilt.c:31-54, via ctypes) over all host cores:
     work items are (channel, band) cascades of a bounded sample of the workload."""
@@ -235,6 +253,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
+    # stdout carries exactly one JSON line: everything libraries print meanwhile (NCCL's version banner, ...) goes
+    # to stderr; the real stdout is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tdt = torch.float64 if esz == 8 else torch.float32
@@ -385,6 +410,8 @@ def main():
     if rank == 0 and not args.no_cpu and world == 1:
         _, _, cpu = cpu_reference_run(2, 1, sos, seconds=10)
 
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -392,8 +419,9 @@ def main():
                           "data": "synthetic (%s)" % ("white noise" if args.signal == "noise" else "log-sine sweep"),
                           "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                           "gpu_launches": int(info["kernels"]) * args.steps, "clocks": clocks,
-                          "launch": info, "gather": gather}))
+                          "launch": info, "gather": gather}), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
