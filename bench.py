@@ -404,6 +404,28 @@ def main():
                "steps": e2e_steps, "channels_per_gpu": Ce,
                "api": "pfb_bank_filter_host (C ABI, pinned host buffers)",
                "checksum": float(yh[0, B // 2, :1000].double().abs().sum())}
+        # the same host input reduced to band energies per 0.1 s inside the kernel (pfb_bank_levels_host): nothing of
+        # size N*B*C crosses the bus, the path is bound by the input copy
+        bl = 4800
+        lev = np.empty((Ce, B, n // bl))
+
+        def lev_step():
+            sth[:] = 0
+            _lib.check(_lib.lib().pfb_bank_levels_host(bank._h, dtype_code, xh.data_ptr(), n, lev.ctypes.data, n // bl,
+                                                       sth.ctypes.data, n, Ce, bl, 0))
+        lev_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            lev_step()
+        dtl = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([dtl], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtl = float(t.item())
+        e2e["band_levels"] = {"value": world * Ce * B * n / dtl, "unit": UNIT, "ms_per_step": dtl * 1e3,
+                              "h2d_bytes_per_step": int(Ce * n * esz + sth.nbytes), "d2h_bytes_per_step": int(lev.nbytes + sth.nbytes),
+                              "api": "pfb_bank_levels_host: band energies per %d samples instead of band signals" % bl}
         del xh, yh
 
     cpu = None

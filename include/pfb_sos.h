@@ -100,6 +100,11 @@ PFB_API int pfb_bank_filter(pfb_bank *bank, int dtype, const void *x, int64_t ld
 PFB_API int pfb_bank_levels(pfb_bank *bank, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
                             void *states, int64_t n, int C, int64_t block_len, int flags, void *stream);
 
+/* pfb_bank_levels on HOST buffers: the input streams through the device in channel groups, only the energies come back
+ * (levels [C*B][ld_levels] on the host).  Synchronous. */
+PFB_API int pfb_bank_levels_host(pfb_bank *bank, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
+                                 void *states, int64_t n, int C, int64_t block_len, int flags);
+
 /* Same on HOST buffers (pageable or pinned): streams the signal through the device in time blocks
  * with carried states, overlapping H2D, kernels and D2H.  Synchronous. */
 PFB_API int pfb_bank_filter_host(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,

@@ -43,6 +43,8 @@ def lib():
         L.pfb_bank_filter.restype = ci
         L.pfb_bank_levels.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, i64, ci, vp]
         L.pfb_bank_levels.restype = ci
+        L.pfb_bank_levels_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, i64, ci]
+        L.pfb_bank_levels_host.restype = ci
         L.pfb_bank_filter_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci]
         L.pfb_bank_filter_host.restype = ci
         L.pfb_bank_last_launch.argtypes = [vp, ctypes.POINTER(LaunchInfo)]
@@ -121,6 +123,10 @@ class Bank:
 
     def levels_ptr(self, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags=0, stream=0):
         check(lib().pfb_bank_levels(self._h, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags, stream))
+
+    def levels_host(self, dtype, x, ldx, levels, ld_lev, states, n, C, block_len, flags=0):
+        check(lib().pfb_bank_levels_host(self._h, dtype, x.ctypes.data, ldx, levels.ctypes.data, ld_lev,
+                                         states.ctypes.data, n, C, block_len, flags))
 
     def filter_host(self, dtype, x, ldx, y, ldy, states, n, C, flags=0):
         check(lib().pfb_bank_filter_host(self._h, dtype, x.ctypes.data, ldx, y.ctypes.data, ldy,

@@ -55,7 +55,19 @@ struct Tables {          // device tables of one (arithmetic type, chunk length)
     long long warm_total = 0;
     double *H = nullptr;      // chunk-impulse-response tables of the GEMM-form pre-pass (pfb_tma.cuh), or null
     long long *Hoff = nullptr;
+    size_t bytes = 0;         // device bytes held (cache accounting)
 };
+
+void free_tables(Tables &t) {
+    for (void *p : t.P) cudaFree(p);
+    for (int *p : t.warm) cudaFree(p);
+    cudaFree(t.H);
+    cudaFree(t.Hoff);
+    t.P.clear();
+    t.warm.clear();
+    t.H = nullptr;
+    t.Hoff = nullptr;
+}
 
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -265,16 +277,13 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
         *out = &it->second;
         return PFB_OK;
     }
-    if (b->tables.size() >= 16) {   // bound the cache; nothing may still be using the old tables
+    size_t cached_bytes = 0;
+    for (auto &kv : b->tables) cached_bytes += kv.second.bytes;
+    // bound the cache (block-wise callers with a fixed block length hit it; the segment loop of the band-level path
+    // and the host-streaming paths add a handful of chunk lengths each); nothing may still be using the old tables
+    if (b->tables.size() >= 96 || cached_bytes > (1ULL << 30)) {
         PFB_CUDA(cudaDeviceSynchronize());
-        for (auto &kv : b->tables) {
-            for (void *p : kv.second.P) cudaFree(p);
-            for (int *p : kv.second.warm) cudaFree(p);
-        cudaFree(kv.second.H);
-        cudaFree(kv.second.Hoff);
-            cudaFree(kv.second.H);
-            cudaFree(kv.second.Hoff);
-        }
+        for (auto &kv : b->tables) free_tables(kv.second);
         b->tables.clear();
     }
     Tables t;
@@ -353,6 +362,7 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
                         dst[(size_t)(step * MT + i / 8) * 32 + (i % 8) * 4 + k] = Hm[(size_t)m * S + i];
                 }
             }
+            t.bytes += (size_t)total * sizeof(double);
             PFB_CUDA(cudaMalloc((void **)&t.H, (size_t)total * sizeof(double)));
             PFB_CUDA(cudaMemcpy(t.H, Hh.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
             PFB_CUDA(cudaMalloc((void **)&t.Hoff, b->rows * sizeof(long long)));
@@ -615,12 +625,7 @@ void pfb_bank_destroy(pfb_bank *b) {
         cudaFree(b->hx[i]);
         cudaFree(b->hy[i]);
     }
-    for (auto &kv : b->tables) {
-        for (void *p : kv.second.P) cudaFree(p);
-        for (int *p : kv.second.warm) cudaFree(p);
-        cudaFree(kv.second.H);
-        cudaFree(kv.second.Hoff);
-    }
+    for (auto &kv : b->tables) free_tables(kv.second);
     delete b;
 }
 
@@ -629,14 +634,7 @@ int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
     std::lock_guard<std::mutex> lock(b->mu);
     if (tol != b->warm_tol) {
         cudaDeviceSynchronize();   // nothing may still be reading the tables built for the old tolerance
-        for (auto &kv : b->tables) {
-            for (void *p : kv.second.P) cudaFree(p);
-            for (int *p : kv.second.warm) cudaFree(p);
-        cudaFree(kv.second.H);
-        cudaFree(kv.second.Hoff);
-            cudaFree(kv.second.H);
-            cudaFree(kv.second.Hoff);
-        }
+        for (auto &kv : b->tables) free_tables(kv.second);
         b->tables.clear();
         b->warm_tol = tol;
     }
@@ -885,6 +883,84 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
     b->last.aligned = p.aligned;
     g_status = PFB_OK;
     return PFB_OK;
+}
+
+// Band levels of HOST signals: channel groups stream through the device (input copy of group g+1 under the kernels
+// of group g); only the energies travel back.  The path is bound by the host-to-device copy of the input.
+int pfb_bank_levels_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
+                         void *states, int64_t n, int C, int64_t block_len, int flags) {
+    if (!b || !x || !levels || !states) return fail(PFB_ERR_INVALID, "pfb_bank_levels_host: null argument");
+    if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_levels_host: bad dtype");
+    if (n <= 0 || C <= 0 || ldx < n || block_len <= 0 || n % block_len != 0 || ld_levels < n / block_len)
+        return fail(PFB_ERR_INVALID, "pfb_bank_levels_host: bad sizes");
+    const size_t esz = dtype == PFB_F64 ? 8 : 4;
+    const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
+    const int B = b->B;
+    const long long nblocks = n / block_len;
+    const long long pitch = (n + 31) / 32 * 32;
+    // groups of at most 1 GiB of input, at least four groups when there are that many channels
+    long long Cg = std::max<long long>(1, std::min<long long>(C, (1LL << 30) / (long long)(pitch * esz)));
+    Cg = std::min<long long>(Cg, std::max<long long>(1, (C + 3) / 4));
+    void *dx[2] = {nullptr, nullptr}, *ds = nullptr;
+    double *dl = nullptr;
+    cudaStream_t sc = nullptr, sh = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
+    int rc = PFB_OK;
+    auto cleanup = [&]() {
+        cudaFree(dx[0]); cudaFree(dx[1]); cudaFree(ds); cudaFree(dl);
+        for (int i = 0; i < 2; ++i) {
+            if (in_done[i]) cudaEventDestroy(in_done[i]);
+            if (used[i]) cudaEventDestroy(used[i]);
+        }
+        if (sc) cudaStreamDestroy(sc);
+        if (sh) cudaStreamDestroy(sh);
+    };
+#define PFB_CUDA_L(call)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            rc = fail(PFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            cleanup();                                                                                    \
+            return rc;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+    PFB_CUDA_L(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+    PFB_CUDA_L(cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PFB_CUDA_L(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+        PFB_CUDA_L(cudaEventCreateWithFlags(&used[i], cudaEventDisableTiming));
+        PFB_CUDA_L(cudaMalloc(&dx[i], (size_t)Cg * pitch * esz));
+    }
+    const size_t nstate = (size_t)C * B * b->K * 2;
+    PFB_CUDA_L(cudaMalloc(&ds, nstate * ssz));
+    PFB_CUDA_L(cudaMalloc((void **)&dl, (size_t)C * B * nblocks * sizeof(double)));
+    PFB_CUDA_L(cudaMemcpyAsync(ds, states, nstate * ssz, cudaMemcpyHostToDevice, sc));
+    const int ngroups = (int)((C + Cg - 1) / Cg);
+    for (int g = 0; g < ngroups; ++g) {
+        const int s = g & 1;
+        const int c0 = (int)(g * Cg), cg = (int)std::min<long long>(Cg, C - c0);
+        if (g >= 2) PFB_CUDA_L(cudaStreamWaitEvent(sh, used[s], 0));      // the slot's previous group has been filtered
+        PFB_CUDA_L(cudaMemcpy2DAsync(dx[s], pitch * esz, (const char *)x + (size_t)c0 * ldx * esz, ldx * esz, n * esz, cg,
+                                     cudaMemcpyHostToDevice, sh));
+        PFB_CUDA_L(cudaEventRecord(in_done[s], sh));
+        PFB_CUDA_L(cudaStreamWaitEvent(sc, in_done[s], 0));
+        rc = pfb_bank_levels(b, dtype, dx[s], pitch, dl + (size_t)c0 * B * nblocks, nblocks,
+                             (char *)ds + (size_t)c0 * B * b->K * 2 * ssz, n, cg, block_len, flags, sc);
+        if (rc) {
+            cleanup();
+            return rc;
+        }
+        PFB_CUDA_L(cudaEventRecord(used[s], sc));
+    }
+    PFB_CUDA_L(cudaMemcpy2DAsync(levels, ld_levels * sizeof(double), dl, nblocks * sizeof(double), nblocks * sizeof(double),
+                                 (size_t)C * B, cudaMemcpyDeviceToHost, sc));
+    PFB_CUDA_L(cudaMemcpyAsync(states, ds, nstate * ssz, cudaMemcpyDeviceToHost, sc));
+    PFB_CUDA_L(cudaStreamSynchronize(sc));
+    PFB_CUDA_L(cudaStreamSynchronize(sh));
+    cleanup();
+    g_status = PFB_OK;
+    return PFB_OK;
+#undef PFB_CUDA_L
 }
 
 // Host-buffer filtering of a shared bank by CHANNEL GROUPS: a group's whole time range is filtered in one call, so

@@ -339,3 +339,23 @@ def test_gammatone_synthesize_golden(pfb):
     yb, _ = gt.fos_bank(xb, gfb._coef_rows, gfb.order)
     out, mem = gfb.synthesize_batch(yb)
     assert rel_l2(out[0].real.cpu().numpy(), g["y_block1"]) <= 1e-12 and float(out.imag.abs().max()) == 0.0
+
+
+def test_bank_levels_host_equals_device(pfb):
+    """pfb_bank_levels_host (numpy in, energies out, channel groups streamed) gives exactly the device entry's result."""
+    import pyfilterbank_b200.sosfiltering as sf
+    from pyfilterbank_b200 import _lib
+    rng = np.random.default_rng(21)
+    ofb = pfb.FractionalOctaveFilterbank(sample_rate=48000)
+    B, K = ofb.num_bands, 4
+    sos = np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6)
+    bank = sf.get_bank(sos)
+    C, n, bl = 9, 38400, 640
+    x = rng.standard_normal((C, n))
+    st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+    e_dev, st_dev = sf.bank_levels(bank, torch.from_numpy(x).cuda(), bl, torch.from_numpy(st0.copy()).cuda())
+    lev = np.empty((C, B, n // bl))
+    st = st0.copy()
+    bank.levels_host(_lib.PFB_F64, x, n, lev, n // bl, st, n, C, bl)
+    assert np.array_equal(lev, e_dev.cpu().numpy())
+    assert np.array_equal(st, st_dev.cpu().numpy())
