@@ -196,10 +196,14 @@ def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
                 times.append(dt)
     per_step = float(np.mean(times))
     value = C * B * n / per_step
+    t0 = time.perf_counter()
+    work(0)                                   # one channel's 33 cascades on one core, for the per-core figure
+    single = B * n / (time.perf_counter() - t0)
     sample = "%d channels x %d bands x %d s @ %d Hz float64 per step, %s via ctypes, %d threads" % (
         C, B, seconds, FS, "oracle/_ref sosfilter_double (unmodified sosfilt.c, gcc -O3)"
         if kind == "reference" else "oracle port", cores)
-    return value, per_step, {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    return value, per_step, {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "single_core_value": single}
 
 
 def main():
