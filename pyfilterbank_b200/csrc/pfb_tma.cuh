@@ -101,6 +101,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+// wait until at most `pending` of this thread's most recent bulk groups have not yet been read from shared memory
+__device__ __forceinline__ void bulk_wait_read_upto(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;\n" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 3;\n" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
@@ -294,25 +303,37 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait(&full[s], ph);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            // the previous tile's TMA stores must have finished reading this warp's output buffer.
-            // (Storing each 128-byte half as soon as it is filtered was measured and is slower: HBM write
-            // efficiency of this scattered-row pattern drops from ~5.0 to ~4.4 TB/s when a row's 256 bytes
-            // arrive as two separate 128-byte bursts; see profiles/r01_ubench_tma_store_rows.txt.)
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
+            // The tile's NH half rows are stored together at the end of the tile: a row's fragment must reach HBM as
+            // one burst (storing each 128-byte half as soon as it is filtered dropped the write efficiency from ~5.0
+            // to ~4.4 TB/s, profiles/r01_ubench_tma_store_rows.txt).  float32: each half is its own bulk group, so half
+            // h of the next tile only waits for the read of half h of this one and filtering overlaps the draining
+            // (4.82 -> 4.68 ms on cfg 2); float64 is bound by the stores themselves and keeps one group (no gain
+            // measured, 9.95 vs 10.05 ms).
+            constexpr bool kSplit = sizeof(T) == 4;
+            if (!kSplit) {
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+            }
             // float32 wide tiles: keep the four half rows a loop (fully unrolled they are ~24 KB of code per
             // warp iteration and the kernel stalls on instruction fetch)
 #pragma unroll(sizeof(T) == 4 && NH == 4 ? 1 : NH)
-            for (int h = 0; h < NH; ++h)
+            for (int h = 0; h < NH; ++h) {
+                if (kSplit) {
+                    if (lane == 0) bulk_wait_read_upto(NH - 1 - h);
+                    __syncwarp();
+                }
                 filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + h * kTileBytes, key, c, wst);
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&empty[s]);
 #pragma unroll
-                for (int h = 0; h < NH; ++h)
+                for (int h = 0; h < NH; ++h) {
                     tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
-                bulk_commit();
+                    if (kSplit) bulk_commit();
+                }
+                if (!kSplit) bulk_commit();
             }
         }
     } else {
