@@ -51,4 +51,45 @@ while time.time() < t_end:
         e2 = max(rel(y2.cpu().numpy()[:, b], yd[:, b]) for b in range(B))
         if not e2 <= 1e-6:
             print("FAIL fd K=%d B=%d C=%d n=%d err=%.2e" % (K, B, C, n, e2)); sys.exit(1)
+# gammatone banks: random batch sizes, lengths and orders through the planner
+from pyfilterbank_b200 import gammatone as gt
+t_end = time.time() + float(os.environ.get("SECONDS_FOS", 30))
+fos_cases = 0
+while time.time() < t_end:
+    order = int(rng.choice([1, 2, 3, 4, 5, 6, 8])); nb = int(rng.integers(1, 30))
+    C = int(rng.choice([1, 2, 5, 16, 33, 64])); n = int(rng.choice([1, 16, 100, 4096, 8000, 30000, 100002]))
+    try:
+        gfb = p.GammatoneFilterbank(samplerate=16000, order=order, startband=-nb // 2, endband=nb - nb // 2 - 1, density=0.7)
+    except IndexError:   # like the reference, the constructor's delay estimate needs the impulse peak inside 20 ms
+        continue
+    x = rng.standard_normal((C, n))
+    y, st = gt.fos_bank(torch.from_numpy(x).cuda(), gfb._coef_rows, order)
+    for i in sorted({0, len(gfb._coeffs) - 1}):
+        b, a = gfb._coeffs[i]
+        for c in sorted({0, C - 1}):
+            y0, s0 = oracle.fosfilter(b, a, order, x[c])
+            e = rel(y[c, i].cpu().numpy(), y0)
+            if not (e <= 1e-10 and rel(st[c, i].cpu().numpy(), s0) <= 1e-9):
+                print("FAIL fos order=%d B=%d C=%d n=%d err=%.2e" % (order, len(gfb._coeffs), C, n, e)); sys.exit(1)
+    fos_cases += 1
+# band levels on random block structures
+t_end = time.time() + float(os.environ.get("SECONDS_LEV", 30))
+lev_cases = 0
+g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "designs.npz"))
+s48 = g["third_48k_o4_sosmat"]; sos48 = np.ascontiguousarray(s48.T).reshape(s48.shape[1], -1, 6)
+bank48 = p.Bank(sos48)
+while time.time() < t_end:
+    C = int(rng.choice([1, 3, 8, 40])); bl = 32 * int(rng.choice([1, 2, 5, 20, 150])); nblk = int(rng.choice([1, 2, 7, 30, 100]))
+    n = bl * nblk
+    if C * 33 * n > 2e8: continue
+    x = rng.standard_normal((C, n))
+    y0, _ = oracle.sos_bank(x, sos48)
+    e0 = (y0.reshape(C, 33, nblk, bl) ** 2).sum(axis=3)
+    e, _ = p.bank_levels(bank48, torch.from_numpy(x).cuda(), bl)
+    e = e.cpu().numpy()
+    scale = e0.max(axis=2, keepdims=True)
+    if not np.max(np.abs(e - e0) / scale) <= 2e-9:
+        print("FAIL levels C=%d bl=%d nblk=%d err=%.2e" % (C, bl, nblk, np.max(np.abs(e - e0) / scale))); sys.exit(1)
+    lev_cases += 1
+print("gammatone cases %d, band-level cases %d" % (fos_cases, lev_cases))
 print("fuzz ok: %d cases, worst band error %.2e, launch kinds (mode, path) %s" % (cases, worst, modes))

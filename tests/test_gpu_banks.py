@@ -359,3 +359,21 @@ def test_bank_levels_host_equals_device(pfb):
     bank.levels_host(_lib.PFB_F64, x, n, lev, n // bl, st, n, C, bl)
     assert np.array_equal(lev, e_dev.cpu().numpy())
     assert np.array_equal(st, st_dev.cpu().numpy())
+
+
+@pytest.mark.parametrize("order", [5, 6, 8])
+def test_gammatone_high_orders_are_not_chunked(pfb, oracle, order):
+    """Cascades of more than four identical poles run one chunk per signal (composing chunk states through the
+    transition of an n-fold pole loses digits: found by scripts/fuzz_shapes.py at order 8)."""
+    from pyfilterbank_b200 import gammatone as gt
+    gfb = pfb.GammatoneFilterbank(samplerate=16000, order=order, startband=-8, endband=8, density=0.7)
+    rng = np.random.default_rng(order)
+    C, n = 16, 100002
+    x = rng.standard_normal((C, n))
+    y, st = gt.fos_bank(torch.from_numpy(x).cuda(), gfb._coef_rows, order)
+    for i in (0, len(gfb._coeffs) - 1):
+        b, a = gfb._coeffs[i]
+        for c in (0, C - 1):
+            y0, s0 = oracle.fosfilter(b, a, order, x[c])
+            assert rel_l2(y[c, i].cpu().numpy(), y0) <= 1e-11, (order, i, c)
+            assert rel_l2(st[c, i].cpu().numpy(), s0) <= 1e-10
