@@ -9,11 +9,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libpfb_sos.so")
+# experiment builds: PFB_VARIANT=name PFB_CFLAGS="-DX=1 ..." -> libpfb_sos_name.so (loaded with PFB_SOS_LIB=<path>)
+VARIANT = os.environ.get("PFB_VARIANT", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libpfb_sos%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"] + os.environ.get("PFB_CFLAGS", "").split()
 
 
 def sources():

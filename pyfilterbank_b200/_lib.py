@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfb_sos.so")
+LIB_PATH = os.environ.get("PFB_SOS_LIB") or os.path.join(_HERE, "libpfb_sos.so")
 
 PFB_F32, PFB_F64 = 0, 1
 MODE_AUTO, MODE_SEQ, MODE_SCAN = 0, 1, 2

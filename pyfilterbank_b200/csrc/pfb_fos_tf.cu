@@ -378,10 +378,6 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     for (int b = 0; b < B; ++b) wproxy[b] = fos_warm(coef_host + 3 * b, order, 1 << 20, 1e-13);
     int J = 0;
     if (const char *v = getenv("PFB_FOS_J")) J = atoi(v);
-    // Cascades of more than four identical poles are not cut into time chunks: the chunk transition of an n-fold pole
-    // has entries ~ L^(n-1) |c|^L / (n-1)!, and composing states through it loses digits (order 8: 3e-7 relative error
-    // found by scripts/fuzz_shapes.py).  One chunk per signal is plain sequential filtering and exact.
-    if (order > 4) J = 1;
     if (J <= 0) {
         const double slots = (wide ? 1.0 : 2.0) * sm_count;
         double best = 1e300;

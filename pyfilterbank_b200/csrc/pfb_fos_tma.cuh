@@ -138,33 +138,35 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
     for (; t < t_mine; ++t) {
         const long long it = t - t_first;
         const int s = (int)(it % kFosStages);
-        mbar_wait(&full[s], (unsigned)((it / kFosStages) & 1));
-        if (lane == 0) mbar_arrive(&empty[s]);
+        mbar_skip_tile(&full[s], &empty[s], (unsigned)((it / kFosStages) & 1), lane);
     }
+    __syncwarp();
     for (; t < nt; ++t) {
         const long long it = t - t_first;
         const int s = (int)(it % kFosStages);
-        mbar_wait(&full[s], (unsigned)((it / kFosStages) & 1));
+        mbar_wait_warp(&full[s], (unsigned)((it / kFosStages) & 1), lane);
         const char *xrow = xs + s * kXStage + lane * kRowBytes;
-        if (PASS_B) {
-            if (lane == 0) bulk_wait_read0();      // the previous tile's stores have read this warp's output buffer
-            __syncwarp();
-        }
+        // every 128-byte output half is its own bulk group: before half k of this tile is overwritten only the
+        // store of half k of the previous tile must have been read, the later halves may still be draining
 #pragma unroll
         for (int h = 0; h < NX; ++h) {
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const double2 in = *reinterpret_cast<const double2 *>(xrow + h * kTileBytes + ((v ^ key) << 4));
-                double yr, yi;
-                fos_sample<ORDER>(in.x, gain, cr, ci, zr, zi, yr, yi);
-                // complex sample 2 v of input half h -> output half 2 h + (2 v) / 8, 16-byte chunk (2 v) % 8
-                if (PASS_B)
-                    *reinterpret_cast<double2 *>(yrow + (2 * h + ((2 * v) >> 3)) * kTileBytes + ((((2 * v) & 7) ^ key) << 4)) =
-                        make_double2(yr, yi);
-                fos_sample<ORDER>(in.y, gain, cr, ci, zr, zi, yr, yi);
-                if (PASS_B)
-                    *reinterpret_cast<double2 *>(yrow + (2 * h + ((2 * v + 1) >> 3)) * kTileBytes +
-                                                 ((((2 * v + 1) & 7) ^ key) << 4)) = make_double2(yr, yi);
+            for (int part = 0; part < 2; ++part) {
+                if (PASS_B) {
+                    if (lane == 0) bulk_wait_read_upto(2 * NX - 1 - (2 * h + part));
+                    __syncwarp();
+                }
+                char *yhalf = yrow + (2 * h + part) * kTileBytes;
+#pragma unroll
+                for (int v = 4 * part; v < 4 * part + 4; ++v) {
+                    const double2 in = *reinterpret_cast<const double2 *>(xrow + h * kTileBytes + ((v ^ key) << 4));
+                    double yr, yi;
+                    fos_sample<ORDER>(in.x, gain, cr, ci, zr, zi, yr, yi);
+                    // complex sample 2 v of input half h -> output half 2 h + part, 16-byte chunk (2 v) % 8
+                    if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v) & 7) ^ key) << 4)) = make_double2(yr, yi);
+                    fos_sample<ORDER>(in.y, gain, cr, ci, zr, zi, yr, yi);
+                    if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v + 1) & 7) ^ key) << 4)) = make_double2(yr, yi);
+                }
             }
         }
         if (PASS_B) fence_proxy_async();
@@ -173,9 +175,10 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
             mbar_arrive(&empty[s]);
             if (PASS_B) {
 #pragma unroll
-                for (int h = 0; h < 2 * NX; ++h)
+                for (int h = 0; h < 2 * NX; ++h) {
                     tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(2 * t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
-                bulk_commit();
+                    bulk_commit();
+                }
             }
         }
     }

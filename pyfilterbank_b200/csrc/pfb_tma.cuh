@@ -81,6 +81,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+// Wait of a whole consumer warp: one lane polls, the warp re-converges on __syncwarp(), then every lane performs
+// its own (immediately successful) wait so that each of them has acquired the phase.
+// Polling with all 32 lanes in the spin loop of mbar_wait() turned out NOT to be equivalent.  Measured
+// (scripts/ubench/fos_race.cu, profiles/r01h_fos_race.txt): with 3-4 CTAs resident per SM the gammatone pre-pass
+// gave 2-10 k of 1 M chunk states that differed between runs of the same launch; with one CTA per SM, or with this
+// wait, none.  ptxas compiles the all-lane loop as if the warp were converged behind it (every later __syncwarp()
+// disappears from the SASS), so lanes that leave the loop apart are never joined again and the stragglers read a
+// stage after lane 0 has already released it to the producer -- the most likely mechanism; the fix is the
+// measured part.
+#ifndef PFB_WAIT_MODE
+#define PFB_WAIT_MODE 2
+#endif
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, unsigned parity, int lane) {
+#if PFB_WAIT_MODE == 0
+    mbar_wait(bar, parity);
+#else
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+#if PFB_WAIT_MODE == 2
+    mbar_wait(bar, parity);
+#endif
+#endif
+}
+// Tiles that are only released (not read): lane 0 waits and arrives alone, the rest of the warp does nothing.
+__device__ __forceinline__ void mbar_skip_tile(uint64_t *full_bar, uint64_t *empty_bar, unsigned parity, int lane) {
+    if (lane == 0) {
+        mbar_wait(full_bar, parity);
+        mbar_arrive(empty_bar);
+    }
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::
@@ -282,7 +312,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % NS);
             const unsigned ph = (unsigned)((t / NS) & 1);
-            mbar_wait(&full[s], ph);
+            mbar_wait_warp(&full[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             A acc = A(0);
 #pragma unroll
@@ -301,27 +331,21 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % NS);
             const unsigned ph = (unsigned)((t / NS) & 1);
-            mbar_wait(&full[s], ph);
+            mbar_wait_warp(&full[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             // The tile's NH half rows are stored together at the end of the tile: a row's fragment must reach HBM as
             // one burst (storing each 128-byte half as soon as it is filtered dropped the write efficiency from ~5.0
-            // to ~4.4 TB/s, profiles/r01_ubench_tma_store_rows.txt).  float32: each half is its own bulk group, so half
-            // h of the next tile only waits for the read of half h of this one and filtering overlaps the draining
-            // (4.82 -> 4.68 ms on cfg 2); float64 is bound by the stores themselves and keeps one group (no gain
-            // measured, 9.95 vs 10.05 ms).
-            constexpr bool kSplit = sizeof(T) == 4;
-            if (!kSplit) {
-                if (lane == 0) bulk_wait_read0();
-                __syncwarp();
-            }
-            // float32 wide tiles: keep the four half rows a loop (fully unrolled they are ~24 KB of code per
-            // warp iteration and the kernel stalls on instruction fetch)
-#pragma unroll(sizeof(T) == 4 && NH == 4 ? 1 : NH)
+            // to ~4.4 TB/s, profiles/r01_ubench_tma_store_rows.txt).  Each half is its own bulk group, so half h of
+            // the next tile only waits until half h of this one has been read out of shared memory and filtering
+            // overlaps the draining of the other halves.
+            // The half rows stay a loop.  Fully unrolled, the wide float32 tile is ~24 KB of code per warp iteration and
+            // stalls on instruction fetch; and with the warp-level waits above (real WARPSYNCs in the loop) every
+            // fully unrolled variant lost 40-100 % (float64 cfg 2 output pass 15.8 vs 10.0 ms, cfg 3 21.9 vs 11.2 ms,
+            // profiles/r01h_wait_variants.txt), while the rolled loop costs nothing measurable.
+#pragma unroll 1
             for (int h = 0; h < NH; ++h) {
-                if (kSplit) {
-                    if (lane == 0) bulk_wait_read_upto(NH - 1 - h);
-                    __syncwarp();
-                }
+                if (lane == 0) bulk_wait_read_upto(NH - 1 - h);
+                __syncwarp();
                 filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + h * kTileBytes, key, c, wst);
             }
             fence_proxy_async();
@@ -331,9 +355,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
                     tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
-                    if (kSplit) bulk_commit();
+                    bulk_commit();
                 }
-                if (!kSplit) bulk_commit();
             }
         }
     } else {
@@ -342,13 +365,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         for (; t < t_mine; ++t) {
             const long long it = t - t_first;
             const int s = (int)(it % NS);
-            mbar_wait(&full[s], (unsigned)((it / NS) & 1));
-            if (lane == 0) mbar_arrive(&empty[s]);
+            mbar_skip_tile(&full[s], &empty[s], (unsigned)((it / NS) & 1), lane);
         }
+        __syncwarp();
         for (; t < nt; ++t) {
             const long long it = t - t_first;
             const int s = (int)(it % NS);
-            mbar_wait(&full[s], (unsigned)((it / NS) & 1));
+            mbar_wait_warp(&full[s], (unsigned)((it / NS) & 1), lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
 #pragma unroll
             for (int h = 0; h < NH; ++h) filter_half<T, A, K, 0, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst);
@@ -473,9 +496,9 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
     for (; t < t_mine; ++t) {            // tiles before this band's window are only released
         const long long it = t - t_first;
         const int s = (int)(it % kTmaStages);
-        mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
-        if (lane == 0) mbar_arrive(&empty[s]);
+        mbar_skip_tile(&full[s], &empty[s], (unsigned)((it / kTmaStages) & 1), lane);
     }
+    __syncwarp();
     double a_cur[KS][MT];
     if (t < nt) {
 #pragma unroll
@@ -494,7 +517,7 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) a_nxt[ks][mt] = more ? __ldg(Hn + (size_t)(ks * MT + mt) * 32) : 0.0;
-        mbar_wait(&full[s], (unsigned)((it / kTmaStages) & 1));
+        mbar_wait_warp(&full[s], (unsigned)((it / kTmaStages) & 1), lane);
         const char *xt = xlane + s * kStageBytes;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
