@@ -315,7 +315,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             mbar_wait_warp(&full[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             A acc = A(0);
-#pragma unroll
+#pragma unroll 1   // rolled like the output pass (float32 levels: 13.1 ms unrolled, see profiles/r01h_wait_variants.txt)
             for (int h = 0; h < NH; ++h) filter_half<T, A, K, 2, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst, &acc);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -373,7 +373,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const int s = (int)(it % NS);
             mbar_wait_warp(&full[s], (unsigned)((it / NS) & 1), lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < NH; ++h) filter_half<T, A, K, 0, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
