@@ -71,6 +71,30 @@ def test_abi_exports_every_declared_symbol():
     assert b"sm_100a" in L.pfb_version()
 
 
+def test_tma_kernels_keep_their_warp_syncs():
+    """Every kernel that waits on an mbarrier must still contain its __syncwarp()s in the SASS.  When all 32 lanes
+    spun in the try_wait loop, ptxas treated the warp as converged and removed every WARPSYNC -- the cause of the
+    run-to-run differences in profiles/r01h_fos_race.txt (see mbar_wait_warp in pfb_tma.cuh)."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from pyfilterbank_b200 import _lib
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    waits, syncs, name = {}, {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+        elif "SYNCS.PHASECHK" in line:
+            waits[name] = waits.get(name, 0) + 1
+        elif "WARPSYNC" in line:
+            syncs[name] = syncs.get(name, 0) + 1
+    assert len(waits) > 100                      # all instantiations of the TMA kernels
+    # at least: the join after the polling lane, and the join before lane 0 releases the stage
+    bad = [k for k in waits if syncs.get(k, 0) < 2]
+    assert not bad, bad[:3]
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
