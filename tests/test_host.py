@@ -158,3 +158,21 @@ def test_gather_bands_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` needs no GPU: one JSON line on stdout with the driver's keys, timed on the
+    unmodified reference C (oracle/_ref) or, where that is not built, on the port."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["unit"] == "band-samples/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["config"]["workload"].startswith("1/3-octave filter_mimo_c bank, 64 channels x 60 s")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
