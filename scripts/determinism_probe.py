@@ -22,13 +22,10 @@ for C, n in ((64, 480000), (16, 2880000), (3, 1000001)):
             check("sos bank C=%d n=%d %s %s" % (C, n, str(dt)[6:], env or ""), lambda: ofb.filter_mimo_c(x)[0])
             for k in env: del os.environ[k]
         del x
-for order in (1, 2, 4):
+for order in (1, 2, 4, 8):
     gfb = p.GammatoneFilterbank(samplerate=16000, order=order, startband=-11, endband=10, density=0.7)
     for C in (2, 16, 64):
         x = torch.from_numpy(rng.standard_normal((C, 100002))).cuda()
         for J in ("0", "32", "128"):
             os.environ["PFB_FOS_J"] = J
-            for win in ("", "1"):
-                if win: os.environ["PFB_FOS_EXACT_WINDOW"] = "1"
-                else: os.environ.pop("PFB_FOS_EXACT_WINDOW", None)
-                check("gammatone order %d C=%d J=%s exact_window=%s" % (order, C, J, win or "0"), lambda: gt.fos_bank(x, gfb._coef_rows, order)[0])
+            check("gammatone order %d C=%d J=%s" % (order, C, J), lambda: gt.fos_bank(x, gfb._coef_rows, order)[0])
