@@ -15,6 +15,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "pfb_kernels.cuh"
@@ -328,6 +332,31 @@ long long fos_warm(const double *c3, int order, long long L, double tol) {
 
 }  // namespace
 
+// Per-bank tables of the chunked gammatone path, kept between calls: building them costs 4-30 ms of host time per
+// call for 64-96 bands (long double matrix powers and decay windows), more than the kernels of a short block, and
+// uploading them needed a stream synchronisation.  Keyed by device, order and the coefficient bytes; one device
+// buffer [P | warm] per chunk length.
+namespace {
+struct FosTables {
+    void *dev = nullptr;      // P [B][2 order][2 order] doubles, then warm [B] ints at offW
+    size_t offW = 0;
+};
+struct FosPlan {
+    std::vector<long long> wproxy;            // decay windows for the launch planner (independent of the chunk length)
+    std::map<long long, FosTables> by_len;    // chunk length -> tables
+};
+std::mutex g_fos_mu;
+std::map<std::string, FosPlan> g_fos_plans;
+size_t g_fos_tables = 0;
+
+void fos_flush_tables() {    // cudaFree waits for the kernels that still read the buffers
+    for (auto &kv : g_fos_plans)
+        for (auto &t : kv.second.by_len) cudaFree(t.second.dev);
+    g_fos_plans.clear();
+    g_fos_tables = 0;
+}
+}  // namespace
+
 template <int ORDER, int NX>
 static int run_fos_tma_nx(const FosTmaParams &p, const FosCoef &tab, const TmaParams &cp, const CUtensorMap &xmap,
                           const CUtensorMap &ymap, cudaStream_t s) {
@@ -374,8 +403,18 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     const int nb = (B + G0 - 1) / G0, G = (B + nb - 1) / nb;
     // chunks per signal: fill the machine (2 CTAs per SM), prefer few chunks (the pre-pass is cheap: decay windows
     // of gammatone filters are a few thousand samples)
-    std::vector<long long> wproxy(B);
-    for (int b = 0; b < B; ++b) wproxy[b] = fos_warm(coef_host + 3 * b, order, 1 << 20, 1e-13);
+    std::lock_guard<std::mutex> lock(g_fos_mu);
+    std::string key(reinterpret_cast<const char *>(coef_host), (size_t)B * 24);
+    key.append(reinterpret_cast<const char *>(&dev), sizeof(dev));
+    key.append(reinterpret_cast<const char *>(&order), sizeof(order));
+    // bounded: 64 banks / 256 chunk lengths, then start over
+    if ((g_fos_plans.size() >= 64 && !g_fos_plans.count(key)) || g_fos_tables >= 256) fos_flush_tables();
+    FosPlan &plan = g_fos_plans[key];
+    if (plan.wproxy.empty()) {
+        plan.wproxy.resize(B);
+        for (int b = 0; b < B; ++b) plan.wproxy[b] = fos_warm(coef_host + 3 * b, order, 1 << 20, 1e-13);
+    }
+    const std::vector<long long> &wproxy = plan.wproxy;
     int J = 0;
     if (const char *v = getenv("PFB_FOS_J")) J = atoi(v);
     if (J <= 0) {
@@ -418,24 +457,33 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     void *scratch = nullptr;
     cudaError_t e = cudaSuccess;
     if (J > 1) {
-        std::vector<double> P((size_t)B * S * S);
-        std::vector<int> warm(B);
-        for (int b = 0; b < B; ++b) {
-            fos_transition(coef_host + 3 * b, order, Lt, &P[(size_t)b * S * S]);
-            warm[b] = (int)std::min<long long>(fos_warm(coef_host + 3 * b, order, Lt, 1e-13), Lt);
+        FosTables &tb = plan.by_len[Lt];
+        if (!tb.dev) {
+            std::vector<double> P((size_t)B * S * S);
+            std::vector<int> warm(B);
+            for (int b = 0; b < B; ++b) {
+                fos_transition(coef_host + 3 * b, order, Lt, &P[(size_t)b * S * S]);
+                warm[b] = (int)std::min<long long>(fos_warm(coef_host + 3 * b, order, Lt, 1e-13), Lt);
+            }
+            const size_t P_bytes = P.size() * 8, w_bytes = (size_t)B * 4;
+            tb.offW = (P_bytes + 255) / 256 * 256;
+            e = cudaMalloc(&tb.dev, tb.offW + w_bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(tb.dev, P.data(), P_bytes, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy((char *)tb.dev + tb.offW, warm.data(), w_bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                if (tb.dev) cudaFree(tb.dev);
+                plan.by_len.erase(Lt);
+                return (int)e;
+            }
+            ++g_fos_tables;
         }
-        const size_t zs_bytes = (size_t)Q * J * S * 8, P_bytes = P.size() * 8, w_bytes = (size_t)B * 4;
-        const size_t offP = (zs_bytes + 255) / 256 * 256, offW = offP + (P_bytes + 255) / 256 * 256;
-        e = cudaMallocAsync(&scratch, offW + w_bytes, s);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaMemcpyAsync((char *)scratch + offP, P.data(), P_bytes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)scratch + offW, warm.data(), w_bytes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // P / warm are host temporaries
+        const size_t zs_bytes = (size_t)Q * J * S * 8;
+        e = cudaMallocAsync(&scratch, zs_bytes, s);
         if (e != cudaSuccess) return (int)e;
         p.zs = scratch;
-        p.warm = (const int *)((char *)scratch + offW);
+        p.warm = (const int *)((char *)tb.dev + tb.offW);
         cp.zs = scratch;
-        cp.P = (char *)scratch + offP;
+        cp.P = tb.dev;
         cp.states = states;
         cp.Q = (int)Q, cp.B = B, cp.J = J, cp.Ktot = order, cp.k0 = 0;
     }
