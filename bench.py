@@ -206,6 +206,151 @@ def cpu_reference_run(steps, warmup, sos, cores=None, seconds=None):
                              "single_core_value": single}
 
 
+def cpu_extra_baselines(sos, seconds=2):
+    """The other CPU figures SURVEY.md 8(d) asks for, single core, bounded samples: the reference's C through a
+    restatement of its Python wrapper (sosfiltering.py:111-163: three buffer copies around the call), and the
+    scipy.signal.lfilter calls the reference makes for the gammatone bank (gammatone.py:232-236) and the
+    A-weighting prefilter (splweighting.py:80)."""
+    out = {}
+    try:
+        from oracle import oracle as o
+        B, K = sos.shape[:2]
+        n = FS * seconds
+        x = 0.1 * np.random.default_rng(1).standard_normal(n)
+        t0 = time.perf_counter()
+        for b in range(B):
+            o.sosfilter_double_c(x, sos[b], use_ref=o.have_ref())
+        dt = time.perf_counter() - t0
+        out["python_wrapper"] = {"value": B * n / dt, "unit": UNIT, "cores": 1,
+                                 "sample": "33 x sosfilter_double_c (wrapper copies + %s C) on %d s @ %d Hz, 1 channel" % (
+                                     "oracle/_ref" if o.have_ref() else "oracle port", seconds, FS)}
+    except Exception as e:   # the checker is optional for the bench line
+        out["python_wrapper"] = {"error": repr(e)[:200]}
+    try:
+        from scipy.signal import lfilter
+        from pyfilterbank_b200 import gammatone as gt, splweighting as spl
+        gfb_coeffs = list(gt.design_filtbank_coeffs(16000, 4, gt.frequencies_gammatone_bank(-14, 18, 1000.0, 0.5),
+                                                    bandwidth_factor=1.0))
+        n = 16000 * 2
+        x = np.random.default_rng(2).standard_normal(n)
+        t0 = time.perf_counter()
+        for b, a in gfb_coeffs:
+            sig = x
+            bb = b
+            for i in range(4):
+                sig, _ = lfilter(bb, a, sig, zi=[0j])
+                bb = np.ones_like(b)
+        dt = time.perf_counter() - t0
+        out["gammatone_scipy"] = {"value": len(gfb_coeffs) * n / dt, "unit": UNIT, "cores": 1,
+                                  "sample": "%d bands x 4 lfilter passes (gammatone.py:232-236) on 2 s @ 16 kHz" % len(gfb_coeffs)}
+        b, a = spl.a_weighting_coeffs_design(FS)
+        n = FS * 5
+        x = np.random.default_rng(3).standard_normal(n)
+        t0 = time.perf_counter()
+        lfilter(b, a, x)
+        dt = time.perf_counter() - t0
+        out["a_weighting_scipy"] = {"value": n / dt, "unit": "channel-samples/s", "cores": 1,
+                                    "sample": "lfilter(b, a, x) (splweighting.py:80) on 5 s @ 48 kHz"}
+    except Exception as e:
+        out["scipy"] = {"error": repr(e)[:200]}
+    return out
+
+
+def event_time(torch, fn, iters, warm):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def other_configs(torch, pfb, dist, dev, rank, world, peak):
+    """Per-GPU shards of BASELINE.json configs[2..4] (extra keys; the headline is configs[1]): channels / signals
+    are sharded over the ranks, long signals stream in time blocks with carried states, inputs are generated on the
+    device.  Each entry: band-samples/s over all ranks (max time over ranks) and the fraction of the HBM roofline
+    of its algorithmic bytes."""
+    from pyfilterbank_b200 import gammatone as gt, splweighting as spl
+    out = {}
+
+    def finish(name, ms, units_per_rank, alg_bytes_per_rank, extra):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        d = {"value": world * units_per_rank / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+             "roofline_frac": alg_bytes_per_rank / (ms * 1e-3) / 1e9 / peak,
+             "algorithmic_GB_per_gpu": alg_bytes_per_rank / 1e9}
+        d.update(extra)
+        out[name] = d
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    try:   # cfg 5: A-weighting fused with the 1/3-octave bank, 8192 channels sharded, streamed in 0.5 s blocks
+        ofb = pfb.FractionalOctaveFilterbank(sample_rate=FS)
+        B, K = ofb.num_bands, 4
+        bank = pfb.get_bank(np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6))
+        b, a = spl.a_weighting_coeffs_design(FS)
+        C = 8192 // world
+        nblk, blocks = FS // 2, 3
+        for name, tdt, esz in (("cfg5_f32", torch.float32, 4), ("cfg5_f64", torch.float64, 8)):
+            x = torch.randn((C, nblk), generator=gen, device=dev, dtype=tdt) * 0.1
+            y = torch.empty((C, B, nblk), device=dev, dtype=tdt)
+            st = torch.zeros((C, B, K, 2), device=dev, dtype=tdt)
+            wz = torch.zeros((C, 6), device=dev, dtype=torch.float64)
+
+            def run():
+                for _ in range(blocks):      # consecutive blocks of the stream: states and delay values carried
+                    pfb.bank_filter_weighted(bank, x, b, a, st, wz, out=y)
+            ms = event_time(torch, run, 2, 1)
+            finish(name, ms, C * B * nblk * blocks, C * nblk * blocks * esz * (B + 1),
+                   {"workload": "A-weighting + 1/3-octave bank, %d of 8192 channels per GPU, %d blocks of 0.5 s @ 48 kHz "
+                                "with carried states, %s" % (C, blocks, "float32" if esz == 4 else "float64"),
+                    "path": bank.last_launch()["aligned"]})
+            del x, y, st, wz
+            torch.cuda.empty_cache()
+    except Exception as e:
+        out["cfg5_error"] = repr(e)[:300]
+    try:   # cfg 3: 1/12-octave order-6 bank with per-band decimation, 1024 channels sharded, 3 s blocks
+        ofb = pfb.FractionalOctaveFilterbank(sample_rate=FS, order=6, nth_oct=12.0, start_band=-67, end_band=51)
+        C = 1024 // world
+        nblk = 3 * FS
+        load = float((1.0 / ofb.decimation_factors).sum())
+        x = (torch.randn((C, nblk), generator=gen, device=dev, dtype=torch.float64) * 0.1).t()   # (N, C) view
+        state = [None]
+
+        def run():
+            bands, state[0] = ofb.filter_decimated(x, state[0])
+            del bands
+        ms = event_time(torch, run, 2, 1)
+        info = ofb._dec_bank().info()
+        finish("cfg3_decimated", ms, C * ofb.num_bands * nblk, C * nblk * 8 * (1 + load),
+               {"workload": "1/12-octave order-6 bank, per-band decimation, %d of 1024 channels per GPU, 3 s blocks "
+                            "@ 48 kHz with carried states, float64" % C,
+                "band_equivalents": load, "bands": ofb.num_bands, "kernels_per_block": info["last_kernels"],
+                "fused_stages": info["last_fused_stages"]})
+        del x, state
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["cfg3_error"] = repr(e)[:300]
+    try:   # cfg 4: gammatone, 64 ERB bands, 512 signals x 10 s @ 16 kHz sharded over the ranks
+        gfb = gt.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
+        Bg, C, n = len(gfb.centerfrequencies), 512 // world, 160000
+        x = torch.randn((C, n), generator=gen, device=dev, dtype=torch.float64) * 0.1
+        ms = event_time(torch, lambda: gt.fos_bank(x, gfb._coef_rows, 4), 2, 1)
+        finish("cfg4_gammatone", ms, C * Bg * n, C * n * (8 + 16 * Bg),
+               {"workload": "gammatone order 4, %d ERB bands, %d of 512 signals x 10 s @ 16 kHz per GPU, complex128 out" % (Bg, C)})
+        del x
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["cfg4_error"] = repr(e)[:300]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +365,10 @@ def main():
                          "per-channel phase offset (SURVEY.md 8d)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra `configs` block (cfg 3 / 4 / 5 shards)")
+    ap.add_argument("--no-f32", action="store_true", help="skip the float32 lines of the default (float64) run")
+    ap.add_argument("--e2e-channels", type=int, default=32,
+                    help="channels per GPU of the host-buffer (e2e) measurement, the same at every GPU count")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -240,6 +389,10 @@ def main():
         if rank != 0:
             return
         value, per_step, cpu = cpu_reference_run(args.steps, max(args.warmup, 1), sos)
+        config["cpu_sample"] = ("bounded sample of the workload, scaled linearly (the work is exactly linear in channels "
+                                "and samples; sosfilter_double_mimo's 32-bit indices cannot address the full workload): "
+                                + cpu["sample"])
+        cpu.update(cpu_extra_baselines(sos))
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -281,11 +434,14 @@ def main():
         x = (0.5 * torch.sin(phase[None, :] + 2 * np.pi * ch[:, None])).to(tdt)
         del t, phase
     y = torch.empty((C, B, n), device=dev, dtype=tdt)
-    states = torch.zeros((C, B, K, 2), device=dev, dtype=tdt)
+    # float32 signals: the headline runs float64 arithmetic on float32 signals (PFB_ARITH_F64) -- the arithmetic that
+    # meets the 1e-4 tolerance in every band; the pure float32 arithmetic is reported beside it (`f32_arithmetic`)
+    arith64 = esz == 4
+    states = torch.zeros((C, B, K, 2), device=dev, dtype=torch.float64 if arith64 else tdt)
 
     def step():
         states.zero_()
-        pfb.bank_filter(bank, x, states, out=y)
+        pfb.bank_filter(bank, x, states, out=y, arith64=arith64)
 
     def barrier():
         if world > 1:
@@ -335,20 +491,29 @@ def main():
     kms = kt["output"] if kt["calls"] else ms_per_step
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic = None
+    traffic_source = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not arith64:
         with open(tpath) as f:
             tj = json.load(f)
-        # dram bytes per band-sample from the committed ncu capture, scaled to this launch
+        # dram bytes per band-sample from the committed ncu capture, scaled to this launch (NOT measured in this run)
         per_unit = tj.get(args.dtype, {}).get("dram_bytes_per_band_sample")
         if per_unit:
             traffic = per_unit * C * B * n
+            traffic_source = "profiles/traffic.json (one committed ncu --set full capture of this kernel, scaled per band-sample)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src, "kernel": kname,
                 "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
                 "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "kernels_ms": {k: kt[k] for k in ("prepass", "carry", "output", "total")},
                 "kernel_share_of_step": kms / ms_per_step}
+
+    def allmax(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
 
     # optional gather of a bounded slab of band outputs, timed separately (never inside `value`)
     gather = None
@@ -372,26 +537,87 @@ def main():
                   "what": "all_gather_into_tensor (NCCL) of 1 s of every band; reported separately"}
         del full, slab
 
+    # float32 signals on the same workload, both arithmetics, each with its parity (worst band relative L2 against this
+    # library's float64 path -- itself <= 1e-9 of the reference's sosfilt.c in tests/ -- on the float32-rounded input)
+    f32 = None
+    if not args.no_f32:
+        x32 = x if esz == 4 else x.to(torch.float32)
+        npar, cpar = min(n, 20 * FS), min(C, 2)
+        xp = x32[:cpar, :npar].contiguous()
+        yref, _ = pfb.bank_filter(bank, xp.to(torch.float64), None)
+        den = yref.norm(dim=2)
+        if esz == 8:
+            del y
+            torch.cuda.empty_cache()
+            y = torch.empty((C, B, n), device=dev, dtype=torch.float32)
+        f32 = {}
+        for key, a64 in (("arith_f64", True), ("arith_f32", False)):
+            yp, _ = pfb.bank_filter(bank, xp, None, arith64=a64)
+            err = ((yp.to(torch.float64) - yref).norm(dim=2) / den).max(dim=0).values.cpu().numpy()
+            st32 = torch.zeros((C, B, K, 2), device=dev, dtype=torch.float64 if a64 else torch.float32)
+
+            def step32():
+                st32.zero_()
+                pfb.bank_filter(bank, x32, st32, out=y, arith64=a64)
+            ms32 = allmax(event_time(torch, step32, min(args.steps, 10), 3))
+            f32[key] = {"value": world * C * B * n / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32,
+                        "step_frac": C * n * 4 * (B + 1) / (ms32 * 1e-3) / 1e9 / peak,
+                        "path": bank.last_launch()["aligned"],
+                        "parity": {"vs": "float64 path of this library on the float32-rounded input, %d channels x %d s" % (cpar, npar // FS),
+                                   "worst_band_rel_l2": float(err.max()), "bands_within_1e-4": int((err <= 1e-4).sum()),
+                                   "bands": int(B), "tolerance": 1e-4}}
+            del yp, st32
+        f32["note"] = ("arith_f64 = float32 signals, float64 coefficients / states / arithmetic (PFB_ARITH_F64): meets the "
+                       "1e-4 tolerance in every band; arith_f32 = pure float32 arithmetic: like the reference's own "
+                       "float path it misses 1e-4 below ~500 Hz (DF-II states of 1e12, SURVEY.md H3)")
+        del yref, xp, den
+        if esz == 8:
+            del x32
+
     # end to end through the C ABI on host buffers
     e2e = None
     if not args.no_e2e:
         del y
         torch.cuda.empty_cache()
-        e2e_steps = max(1, min(2, args.steps))
-        # one GPU: the whole workload (50 GB of pinned host memory for the band signals); several GPUs share one
-        # host, so every rank streams a 16-channel slice of its workload (12 GB pinned per rank) -- the path is
-        # PCIe-bound either way and `value` counts the band-samples actually moved
-        Ce = C if world == 1 else min(C, 16)
+        e2e_steps = max(1, min(5, args.steps))
+        # The same per-GPU workload at every GPU count: a slice of `e2e-channels` channels of the workload (32: 24 GB
+        # of pinned host memory for the band signals per rank; all ranks share one host).  The path is PCIe-bound, so
+        # the rate does not depend on the slice size; `value` counts the band-samples actually moved.
+        Ce = min(C, args.e2e_channels)
         xh = torch.empty((Ce, n), dtype=tdt, pin_memory=True)
         xh.copy_(x[:Ce].cpu())
         yh = torch.empty((Ce, B, n), dtype=tdt, pin_memory=True)
-        sth = np.zeros((Ce, B, K, 2), dtype=np.float64 if esz == 8 else np.float32)
+        sth = np.zeros((Ce, B, K, 2), dtype=np.float64)      # float32 signals run float64 arithmetic (see above)
         dtype_code = _lib.PFB_F64 if esz == 8 else _lib.PFB_F32
+        e2e_flags = _lib.ARITH_F64 if esz == 4 else 0
+
+        # what the link gives: plain pinned device-to-host copies on all ranks at once (no kernels, 2 GiB each)
+        probe_n = min(yh.numel(), (2 << 30) // esz)
+        dprobe = torch.empty(probe_n, device=dev, dtype=tdt)
+        hprobe = yh.view(-1)[:probe_n]
+        hprobe.copy_(dprobe, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            hprobe.copy_(dprobe, non_blocking=True)
+        torch.cuda.synchronize()
+        rate = 2 * probe_n * esz / (time.perf_counter() - t0) / 1e9
+        del dprobe
+        if world > 1:
+            tr = torch.tensor([rate, -rate], device=dev, dtype=torch.float64)
+            tsum = tr.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            pcie = {"d2h_GBps_per_rank_min": float(-tr[1].item()), "d2h_GBps_per_rank_max": float(tr[0].item()),
+                    "d2h_GBps_aggregate": float(tsum[0].item())}
+        else:
+            pcie = {"d2h_GBps_per_rank_min": rate, "d2h_GBps_per_rank_max": rate, "d2h_GBps_aggregate": rate}
+        pcie["what"] = "plain pinned 2 GiB device-to-host copies, all ranks concurrently, no kernels: the host-side ceiling of e2e"
 
         def e2e_step():
             sth[:] = 0
             _lib.check(_lib.lib().pfb_bank_filter_host(bank._h, dtype_code, xh.data_ptr(), n, yh.data_ptr(), n,
-                                                       sth.ctypes.data, n, Ce, 0))
+                                                       sth.ctypes.data, n, Ce, e2e_flags))
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -406,6 +632,9 @@ def main():
         e2e = {"value": world * Ce * B * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(Ce * n * esz + sth.nbytes),
                "d2h_bytes_per_step": int(Ce * B * n * esz + sth.nbytes), "ms_per_step": dt * 1e3,
                "steps": e2e_steps, "channels_per_gpu": Ce,
+               "config": "%d of the %d channels per GPU x %d s, the same slice at every GPU count" % (Ce, C, args.seconds),
+               "pcie_probe": pcie,
+               "link_frac": (Ce * (B + 1) * n * esz / dt / 1e9) / max(pcie["d2h_GBps_per_rank_min"], 1e-9),
                "api": "pfb_bank_filter_host (C ABI, pinned host buffers)",
                "checksum": float(yh[0, B // 2, :1000].double().abs().sum())}
         # the same host input reduced to band energies per 0.1 s inside the kernel (pfb_bank_levels_host): nothing of
@@ -416,7 +645,7 @@ def main():
         def lev_step():
             sth[:] = 0
             _lib.check(_lib.lib().pfb_bank_levels_host(bank._h, dtype_code, xh.data_ptr(), n, lev.ctypes.data, n // bl,
-                                                       sth.ctypes.data, n, Ce, bl, 0))
+                                                       sth.ctypes.data, n, Ce, bl, e2e_flags))
         lev_step()
         barrier()
         t0 = time.perf_counter()
@@ -432,18 +661,32 @@ def main():
                               "api": "pfb_bank_levels_host: band energies per %d samples instead of band signals" % bl}
         del xh, yh
 
+    configs = None
+    if not args.no_configs:
+        try:
+            del y
+        except NameError:
+            pass
+        del x
+        torch.cuda.empty_cache()
+        configs = other_configs(torch, pfb, dist, dev, rank, world, peak)
+
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
         _, _, cpu = cpu_reference_run(2, 1, sos, seconds=10)
+        cpu.update(cpu_extra_baselines(sos))
+        config["cpu_sample"] = "cpu_baseline is timed on a bounded sample and scaled linearly: " + cpu["sample"]
 
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype if esz == 8 else "f32 signals, f64 arithmetic",
                           "data": "synthetic (%s)" % ("white noise" if args.signal == "noise" else "log-sine sweep"),
                           "config": config, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                          "e2e_band_levels": None if e2e is None else e2e.get("band_levels"),
+                          "f32": f32, "configs": configs,
                           "gpu_launches": int(info["kernels"]) * args.steps, "clocks": clocks,
                           "launch": info, "gather": gather}), flush=True)
     if world > 1:

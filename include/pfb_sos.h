@@ -125,7 +125,8 @@ typedef struct pfb_launch_info {
     int64_t chunk;        /* samples per time chunk (scan mode), n in seq mode */
     int64_t warm_total;   /* sum over cascades of pre-pass samples per chunk (scan mode) */
     int aligned;          /* 0 / 1: cp.async kernels without / with 16-byte vectors; 2: TMA kernels; 3: TMA kernels
-                             with the 512-byte-fragment output pass */
+                             with the 512-byte-fragment output pass; 4: TMA kernels with the fused weighting warp;
+                             5: TMA kernels with a decimating band */
 } pfb_launch_info;
 PFB_API int pfb_bank_last_launch(const pfb_bank *bank, pfb_launch_info *info);
 
@@ -162,6 +163,69 @@ PFB_API int pfb_gt_synthesize_c128(const double *bands, int64_t ldb, double *out
  * values in/out (zeros for the reference's behaviour). */
 PFB_API int pfb_tf_filter_f64(const double *x, int64_t ldx, double *y, int64_t ldy, const double *b, int nb,
                               const double *a, int na, double *z, int64_t n, int R, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Fused callers of the bank (a8, a6', f2).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* FractionalOctaveFilterbank.filter_mimo_c on the SPL-weighted signal as ONE call: y = bank(lfilter(b, a, x)) with
+ * lfilter the reference's weighting prefilter (splweighting.weight_signal, splweighting.py:61-80: direct form II
+ * transposed, scipy's operation order, float64 arithmetic also for float32 signals).  With enough channels
+ * (32-channel blocks x band groups fill the machine) the prefilter runs as one more warp inside the bank kernel on
+ * the shared-memory input tiles and the weighted signal never touches HBM; otherwise the weighting kernel and the
+ * time-chunked bank run back to back on a scratch buffer.  DEVICE pointers, asynchronous on `stream`.
+ *   wb / wa : HOST taps (at most 8 each, normalised by wa[0] like scipy does)
+ *   wz      : DEVICE [C][max(nwb, nwa) - 1] delay values in scipy's zi convention, in/out (zeros = the reference's call)
+ * Everything else as in pfb_bank_filter (flags: mode / PFB_EXACT / PFB_ARITH_F64). */
+PFB_API int pfb_bank_filter_weighted(pfb_bank *bank, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
+                                     void *states, const double *wb, int nwb, const double *wa, int nwa, double *wz,
+                                     int64_t n, int C, int flags, void *stream);
+
+/* Decimating band path (opt-in; the reference has no resampling): stage m = 0 .. nstages - 1
+ * runs at fs / 2^m; the stage m + 1 signal is the stage m signal through the anti-alias cascade `aa_sos`, every
+ * second sample kept.  One call filters all stages: per stage ONE pass over the stage signal produces the stage's
+ * band signals and (as one more band warp with a decimating store) the next stage's signal.
+ *   bands_per_stage[m], sos_per_stage[m] : HOST [bands][K][6] (null for a stage without bands)
+ *   aa_sos : HOST [Kaa][6]                                                                                   */
+typedef struct pfb_decbank pfb_decbank;
+PFB_API int pfb_decbank_create(pfb_decbank **out, int nstages, const int *bands_per_stage,
+                               const double *const *sos_per_stage, int K, const double *aa_sos, int Kaa);
+PFB_API void pfb_decbank_destroy(pfb_decbank *dec);
+/* x DEVICE [C][ldx] float64, n samples; y[m] DEVICE [C][bands m][ldy[m]] receives n_m samples per row with n_0 = n,
+ * n_{m+1} = (n_m - phase_m + 1) / 2; band_states[m] DEVICE [C][bands m][K][2]; aa_states DEVICE
+ * [nstages - 1][C][Kp][2] (Kp from pfb_decbank_info: the anti-alias cascade padded with pass-through sections);
+ * phases HOST [nstages - 1] decimator phases, in/out.  flags: mode / PFB_EXACT.  Asynchronous on `stream`. */
+PFB_API int pfb_decbank_filter(pfb_decbank *dec, const double *x, int64_t ldx, void *const *y, const int64_t *ldy,
+                               void *const *band_states, double *aa_states, int *phases, int64_t n, int C, int flags,
+                               void *stream);
+PFB_API int pfb_decbank_info(const pfb_decbank *dec, int *stages, int *aa_sections_padded, int *last_kernels,
+                             int *last_fused_stages);
+
+/* Streaming session: block-wise filtering of HOST audio with carried, device-resident states (what the reference's
+ * `states` arguments exist for: blockprocessing.py:3-72, sosfiltering.py:143-147).  Streams, events, staging slots
+ * and the state array are created once; pfb_stream_push enqueues input copy, kernels and output copy of one block
+ * and returns (asynchronous for page-locked host buffers; the buffers must stay valid until pfb_stream_sync).  Blocks
+ * of one length allocate nothing after the first.  x HOST [C][ldx], y HOST [C][B][ldy], n <= max_block samples. */
+typedef struct pfb_stream pfb_stream;
+typedef struct pfb_stream_info {
+    int64_t blocks, samples;
+    int64_t device_allocs_total;              /* device allocations of this library since pfb_stream_create */
+    int64_t device_allocs_after_first_block;  /* ... since the first pfb_stream_push returned */
+} pfb_stream_info;
+PFB_API int pfb_stream_create(pfb_stream **out, pfb_bank *bank, int dtype, int C, int64_t max_block, int flags);
+PFB_API int pfb_stream_push(pfb_stream *s, const void *x, int64_t ldx, void *y, int64_t ldy, int64_t n);
+PFB_API int pfb_stream_sync(pfb_stream *s);
+/* wait until the output of push number `block` (0-based) is in host memory, later pushes may still be in flight */
+PFB_API int pfb_stream_wait(pfb_stream *s, int64_t block);
+/* copy the carried states [C][B][K][2] to (set = 0) or from (set = 1) a HOST array; synchronises the session */
+PFB_API int pfb_stream_states(pfb_stream *s, void *states_host, int set);
+PFB_API int pfb_stream_stats(pfb_stream *s, pfb_stream_info *info);
+PFB_API void pfb_stream_destroy(pfb_stream *s);
+
+/* A bank keeps chunk-state scratch per CUDA stream it has been used on; call this before destroying a stream. */
+PFB_API int pfb_bank_release_stream(pfb_bank *bank, void *stream);
+/* device allocations made by this library so far (diagnostics / tests) */
+PFB_API long long pfb_device_allocs(void);
 
 PFB_API const char *pfb_version(void);
 

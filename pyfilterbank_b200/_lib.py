@@ -23,6 +23,11 @@ class LaunchInfo(ctypes.Structure):
                 ("chunk", ctypes.c_int64), ("warm_total", ctypes.c_int64), ("aligned", ctypes.c_int)]
 
 
+class StreamInfo(ctypes.Structure):
+    _fields_ = [("blocks", ctypes.c_int64), ("samples", ctypes.c_int64), ("device_allocs_total", ctypes.c_int64),
+                ("device_allocs_after_first_block", ctypes.c_int64)]
+
+
 _lib = None
 
 
@@ -61,6 +66,34 @@ def lib():
         L.pfb_gt_synthesize_c128.restype = ci
         L.pfb_tf_filter_f64.argtypes = [vp, i64, vp, i64, vp, ci, vp, ci, vp, i64, ci, vp]
         L.pfb_tf_filter_f64.restype = ci
+        L.pfb_bank_filter_weighted.argtypes = [vp, ci, vp, i64, vp, i64, vp, vp, ci, vp, ci, vp, i64, ci, ci, vp]
+        L.pfb_bank_filter_weighted.restype = ci
+        L.pfb_bank_release_stream.argtypes = [vp, vp]
+        L.pfb_bank_release_stream.restype = ci
+        L.pfb_device_allocs.restype = ctypes.c_longlong
+        L.pfb_decbank_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(ci), ctypes.POINTER(vp), ci, vp, ci]
+        L.pfb_decbank_create.restype = ci
+        L.pfb_decbank_destroy.argtypes = [vp]
+        L.pfb_decbank_destroy.restype = None
+        L.pfb_decbank_filter.argtypes = [vp, vp, i64, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(vp), vp,
+                                         ctypes.POINTER(ci), i64, ci, ci, vp]
+        L.pfb_decbank_filter.restype = ci
+        L.pfb_decbank_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.pfb_decbank_info.restype = ci
+        L.pfb_stream_create.argtypes = [ctypes.POINTER(vp), vp, ci, ci, i64, ci]
+        L.pfb_stream_create.restype = ci
+        L.pfb_stream_push.argtypes = [vp, vp, i64, vp, i64, i64]
+        L.pfb_stream_push.restype = ci
+        L.pfb_stream_sync.argtypes = [vp]
+        L.pfb_stream_sync.restype = ci
+        L.pfb_stream_wait.argtypes = [vp, i64]
+        L.pfb_stream_wait.restype = ci
+        L.pfb_stream_states.argtypes = [vp, vp, ci]
+        L.pfb_stream_states.restype = ci
+        L.pfb_stream_stats.argtypes = [vp, ctypes.POINTER(StreamInfo)]
+        L.pfb_stream_stats.restype = ci
+        L.pfb_stream_destroy.argtypes = [vp]
+        L.pfb_stream_destroy.restype = None
         L.pfb_last_error.restype = ctypes.c_char_p
         L.pfb_last_status.restype = ci
         L.pfb_version.restype = ctypes.c_char_p
@@ -121,6 +154,11 @@ class Bank:
     def filter_ptr(self, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags=0, stream=0):
         check(lib().pfb_bank_filter(self._h, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, n, C, flags, stream))
 
+    def filter_weighted_ptr(self, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, b, a, wz_ptr, n, C, flags=0, stream=0):
+        """Weighting prefilter lfilter(b, a, .) + bank as one call (pfb_bank_filter_weighted); b, a numpy float64."""
+        check(lib().pfb_bank_filter_weighted(self._h, dtype, x_ptr, ldx, y_ptr, ldy, states_ptr, b.ctypes.data, len(b),
+                                             a.ctypes.data, len(a), wz_ptr, n, C, flags, stream))
+
     def levels_ptr(self, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags=0, stream=0):
         check(lib().pfb_bank_levels(self._h, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags, stream))
 
@@ -150,3 +188,81 @@ class Bank:
         info = LaunchInfo()
         check(lib().pfb_bank_last_launch(self._h, ctypes.byref(info)))
         return {k: getattr(info, k) for k, _ in LaunchInfo._fields_}
+
+
+class DecBank:
+    """Decimating band path as one C call (pfb_decbank_*): `stage_sos[m]` is (B_m, K, 6) or None for a stage without
+    bands, `aa_sos` (Kaa, 6) the anti-alias cascade applied before every halving."""
+
+    def __init__(self, stage_sos, K, aa_sos):
+        self.nstages = len(stage_sos)
+        self.K = int(K)
+        self.nb = [0 if s is None else int(s.shape[0]) for s in stage_sos]
+        self._keep = [None if s is None else np.ascontiguousarray(s, dtype=np.float64) for s in stage_sos]
+        aa = np.ascontiguousarray(aa_sos, dtype=np.float64).reshape(-1, 6)
+        nbands = (ctypes.c_int * self.nstages)(*self.nb)
+        ptrs = (ctypes.c_void_p * self.nstages)(*[None if s is None else s.ctypes.data for s in self._keep])
+        h = ctypes.c_void_p()
+        check(lib().pfb_decbank_create(ctypes.byref(h), self.nstages, nbands, ptrs, self.K, aa.ctypes.data, aa.shape[0]))
+        self._h = h
+        self.Kp = self.info()["aa_sections_padded"]
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.pfb_decbank_destroy(h)
+
+    def info(self):
+        v = [ctypes.c_int() for _ in range(4)]
+        check(lib().pfb_decbank_info(self._h, *[ctypes.byref(x) for x in v]))
+        return {"stages": v[0].value, "aa_sections_padded": v[1].value, "last_kernels": v[2].value,
+                "last_fused_stages": v[3].value}
+
+    def filter_ptr(self, x_ptr, ldx, y_ptrs, ldys, state_ptrs, aa_states_ptr, phases, n, C, flags=0, stream=0):
+        """phases: list of ints (decimator phase per halving stage), updated in place."""
+        S = self.nstages
+        yp = (ctypes.c_void_p * S)(*y_ptrs)
+        ld = (ctypes.c_int64 * S)(*ldys)
+        sp = (ctypes.c_void_p * S)(*state_ptrs)
+        ph = (ctypes.c_int * max(S - 1, 1))(*(list(phases) + [0])[:max(S - 1, 1)])
+        check(lib().pfb_decbank_filter(self._h, x_ptr, ldx, yp, ld, sp, aa_states_ptr, ph, n, C, flags, stream))
+        for i in range(S - 1):
+            phases[i] = int(ph[i])
+
+
+class Stream:
+    """Streaming session over host buffers (pfb_stream_*): device-resident states, asynchronous pushes."""
+
+    def __init__(self, bank, dtype, C, max_block, flags=0):
+        self.bank = bank                      # keeps the bank alive
+        h = ctypes.c_void_p()
+        check(lib().pfb_stream_create(ctypes.byref(h), bank._h, dtype, C, max_block, flags))
+        self._h = h
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.pfb_stream_destroy(h)
+
+    __del__ = close
+
+    def push(self, x_ptr, ldx, y_ptr, ldy, n):
+        check(lib().pfb_stream_push(self._h, x_ptr, ldx, y_ptr, ldy, n))
+
+    def sync(self):
+        check(lib().pfb_stream_sync(self._h))
+
+    def wait(self, block):
+        check(lib().pfb_stream_wait(self._h, block))
+
+    def get_states(self, out):
+        check(lib().pfb_stream_states(self._h, out.ctypes.data, 0))
+        return out
+
+    def set_states(self, arr):
+        check(lib().pfb_stream_states(self._h, arr.ctypes.data, 1))
+
+    def stats(self):
+        info = StreamInfo()
+        check(lib().pfb_stream_stats(self._h, ctypes.byref(info)))
+        return {k: getattr(info, k) for k, _ in StreamInfo._fields_}

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -18,6 +19,7 @@
 #include "../../include/pfb_sos.h"
 #include "pfb_kernels.cuh"
 #include "pfb_tma.cuh"
+#include "pfb_tf.cuh"
 
 namespace {
 
@@ -74,6 +76,36 @@ int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+// Every device allocation of this translation unit goes through here, so callers (the streaming session's
+// statistics, tests/test_gpu_stream.py) can verify that steady-state block processing allocates nothing.
+std::atomic<long long> g_device_allocs{0};
+cudaError_t counted_malloc(void **p, size_t bytes) {
+    ++g_device_allocs;
+    return cudaMalloc(p, bytes);
+}
+template <typename P> cudaError_t counted_malloc(P **p, size_t bytes) { return counted_malloc((void **)p, bytes); }
+cudaError_t counted_malloc_async(void **p, size_t bytes, cudaStream_t s) {
+    ++g_device_allocs;
+    return cudaMallocAsync(p, bytes, s);
+}
+
+// Optional stages fused into one bank pass (TMA kernels only; see TmaParams).
+struct FilterExtra {
+    // SPL-weighting prefilter ahead of the bank: taps normalised (wa[0] == 1), wz [C][wnz] device delay values in/out
+    int wnz = 0;
+    double wb[8] = {}, wa[8] = {};
+    double *wz = nullptr;
+    // the LAST band of the bank stores every second sample (parity dec_phase) to y2 [C][ldy2]; its states are
+    // dec_states [C][K][2], y and `states` hold the other B - 1 bands
+    bool dec = false;
+    int dec_phase = 0;
+    void *y2 = nullptr;
+    long long ldy2 = 0;
+    void *dec_states = nullptr;
+    long long n_done = 0;    // out: samples filtered (a multiple of the tile step; the caller finishes the ragged end)
+};
+constexpr int kNotApplicable = 1;   // bank_filter_locked with a FilterExtra: the shapes do not fit the fused path
+
 }  // namespace
 
 struct pfb_bank {
@@ -100,6 +132,12 @@ struct pfb_bank {
     size_t hx_bytes = 0, hy_bytes = 0;
     double *gains_dev[2] = {nullptr, nullptr};   // gain tables when no chunk tables are needed (single chunk)
     double *gains_only(int arith);
+    // streams and events of the host-buffer entry points (pfb_bank_filter_host, pfb_bank_levels_host), created once
+    // per bank: the per-stream scratch above is keyed by stream handle, so these must not change between calls
+    std::mutex host_mu;                          // one host-buffer call per bank at a time (they share the staging slots)
+    cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // compute, drain (D2H), input (H2D)
+    cudaEvent_t hev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ensure_host_ctx();
 
     cudaEvent_t tev_new() {
         cudaEvent_t e = nullptr;
@@ -108,6 +146,13 @@ struct pfb_bank {
         return e;
     }
 };
+
+int pfb_bank::ensure_host_ctx() {
+    if (hs[0]) return PFB_OK;
+    for (cudaStream_t &st : hs) PFB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : hev) PFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return PFB_OK;
+}
 
 // Gain tables of the normalised float64 arithmetic (single-sweep banks with well-scaled b0 only):
 // [rows][K][2] = (G_k, 1 / G_k), G_k = b0_0 ... b0_{k-1}.  Null: plain arithmetic.
@@ -128,10 +173,10 @@ double *pfb_bank::gains_only(int arith) {
         }
     }
     if (!ok) {
-        cudaMalloc((void **)&gains_dev[1], 8);
+        counted_malloc((void **)&gains_dev[1], 8);
         return nullptr;
     }
-    if (cudaMalloc((void **)&gains_dev[0], g.size() * sizeof(double)) != cudaSuccess) return nullptr;
+    if (counted_malloc((void **)&gains_dev[0], g.size() * sizeof(double)) != cudaSuccess) return nullptr;
     cudaMemcpy(gains_dev[0], g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice);
     return gains_dev[0];
 }
@@ -236,11 +281,11 @@ int ensure_coef(pfb_bank *b, int arith) {
     const std::vector<double> &c = b->coef_host;
     void *d = nullptr;
     if (arith == PFB_F64) {
-        PFB_CUDA(cudaMalloc(&d, n * sizeof(double)));
+        PFB_CUDA(counted_malloc(&d, n * sizeof(double)));
         PFB_CUDA(cudaMemcpy(d, c.data(), n * sizeof(double), cudaMemcpyHostToDevice));
     } else {
         std::vector<float> f(c.begin(), c.end());
-        PFB_CUDA(cudaMalloc(&d, n * sizeof(float)));
+        PFB_CUDA(counted_malloc(&d, n * sizeof(float)));
         PFB_CUDA(cudaMemcpy(d, f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     }
     b->coef[arith] = d;
@@ -316,16 +361,16 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
             t.warm_total += std::min<long long>(warm[r], L);
         }
         int *dw = nullptr;
-        PFB_CUDA(cudaMalloc(&dw, b->rows * sizeof(int)));
+        PFB_CUDA(counted_malloc(&dw, b->rows * sizeof(int)));
         PFB_CUDA(cudaMemcpy(dw, warm.data(), b->rows * sizeof(int), cudaMemcpyHostToDevice));
         t.warm.push_back(dw);
         void *d = nullptr;
         if (arith == PFB_F64) {
-            PFB_CUDA(cudaMalloc(&d, n * sizeof(double)));
+            PFB_CUDA(counted_malloc(&d, n * sizeof(double)));
             PFB_CUDA(cudaMemcpy(d, Pd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
         } else {
             std::vector<float> Pf(Pd.begin(), Pd.end());
-            PFB_CUDA(cudaMalloc(&d, n * sizeof(float)));
+            PFB_CUDA(counted_malloc(&d, n * sizeof(float)));
             PFB_CUDA(cudaMemcpy(d, Pf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         }
         t.P.push_back(d);
@@ -363,9 +408,9 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
                 }
             }
             t.bytes += (size_t)total * sizeof(double);
-            PFB_CUDA(cudaMalloc((void **)&t.H, (size_t)total * sizeof(double)));
+            PFB_CUDA(counted_malloc((void **)&t.H, (size_t)total * sizeof(double)));
             PFB_CUDA(cudaMemcpy(t.H, Hh.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
-            PFB_CUDA(cudaMalloc((void **)&t.Hoff, b->rows * sizeof(long long)));
+            PFB_CUDA(counted_malloc((void **)&t.Hoff, b->rows * sizeof(long long)));
             PFB_CUDA(cudaMemcpy(t.Hoff, off.data(), b->rows * sizeof(long long), cudaMemcpyHostToDevice));
         }
     }
@@ -490,7 +535,7 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
 // One (pre-pass, carry, output | levels) launch set over J chunks of Lt samples.  Caller holds b->mu.
 static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long long ldx, void *y, long long ldy, void *states,
                    long long Lt, int J, int C, int nb, int G, cudaStream_t stream, double *levels, long long lev_ld,
-                   long long lev_off, int ut, bool may_time, bool wide = false) {
+                   long long lev_off, int ut, bool may_time, bool wide = false, const FilterExtra *ex = nullptr) {
     const int arith = arith64 ? PFB_F64 : PFB_F32;
     const int tt = 2 * pfb::kRowBytes / (dtype == PFB_F64 ? 8 : 4);
     const int JR = std::min(J, 32), CH = 32 / JR;
@@ -510,17 +555,29 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
             cudaFree(ws.first);
             ws = {nullptr, 0};
         }
-        PFB_CUDA(cudaMalloc(&ws.first, need));
+        PFB_CUDA(counted_malloc(&ws.first, need));
         ws.second = need;
     }
     const bool timed = may_time && b->timing_left > 0;
     if (timed) { --b->timing_left; ++b->timing_calls; }
-    CUtensorMap xmap, ymap;
+    const bool dec = ex && ex->dec;
+    const bool weighted = ex && ex->wnz > 0;
+    CUtensorMap xmap, ymap, ymap2;
     if (!pfb::make_x_map(&xmap, dtype, x, Lt, J, C, ldx, JR, CH)) return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-    if (y) {
-        if (!pfb::make_y_map(&ymap, dtype, y, Lt, J, b->B, C, ldy, JR, CH)) return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    const int By = dec ? b->B - 1 : b->B;   // bands stored through the main output map
+    if (y && By > 0) {
+        if (!pfb::make_y_map(&ymap, dtype, y, Lt, J, By, C, ldy, JR, CH)) return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     } else {
-        ymap = xmap;   // band-level epilogue: nothing is stored through it
+        ymap = xmap;   // band-level epilogue / decimating band only: nothing is stored through it
+    }
+    ymap2 = ymap;
+    if (dec && !pfb::make_y_map(&ymap2, dtype, ex->y2, Lt / 2, J, 1, C, ex->ldy2, JR, CH))
+        return fail(PFB_ERR_CUDA, "cuTensorMapEncodeTiled failed (decimated output)");
+    double *wz_copy = nullptr;
+    if (weighted) {   // the kernel reads the start values from a copy: band group 0 overwrites wz while others may not have started
+        PFB_CUDA(counted_malloc_async((void **)&wz_copy, (size_t)C * 8 * sizeof(double), stream));
+        PFB_CUDA(cudaMemcpy2DAsync(wz_copy, 8 * sizeof(double), ex->wz, ex->wnz * sizeof(double), ex->wnz * sizeof(double),
+                                   (size_t)C, cudaMemcpyDeviceToDevice, stream));
     }
     pfb::TmaParams tp{};
     tp.zs = ws.first;
@@ -532,6 +589,19 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     tp.nb_a = nb;
     tp.levels = levels, tp.lev_ld = lev_ld, tp.lev_off = lev_off, tp.ut = ut;
     tp.wide = wide ? 1 : 0;
+    if (weighted) {
+        tp.weighted = 1;
+        tp.wnz = ex->wnz;
+        tp.wz_in = wz_copy;
+        tp.wz = ex->wz;
+        for (int k = 0; k < 8; ++k) tp.wb[k] = ex->wb[k], tp.wa[k] = ex->wa[k];
+    }
+    if (dec) {
+        tp.dec_band1 = b->B;       // the last band
+        tp.dec_phase = ex->dec_phase;
+        tp.Bs = b->B - 1;
+        tp.dec_states = ex->dec_states;
+    }
     if (tab) {
         tp.P = tab->P[0];
         tp.warm = tab->warm[0];
@@ -549,9 +619,10 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
         for (cudaEvent_t &e : ev) e = b->tev_new();
     int launches = 0;
     const double *ch = b->coef_host.data();
-    int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
-              : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3)
-                              : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, stream, &launches, timed ? ev : nullptr, 3);
+    int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3)
+              : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3)
+                              : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3);
+    if (wz_copy) cudaFreeAsync(wz_copy, stream);
     if (err != 0) return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
     if (timed) {
         b->trecs.push_back({ev[0], ev[1], 0});
@@ -565,7 +636,9 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     b->last.warps_per_cascade = J / JR;
     b->last.chunk = Lt;
     b->last.warm_total = tab ? tab->warm_total * C : 0;
-    b->last.aligned = wide ? 3 : 2;   // 2 = TMA path, 3 = TMA path with the wide (512-byte fragment) output pass
+    // 2 = TMA path, 3 = with the wide (512-byte fragment) output pass, 4 = with the fused weighting warp,
+    // 5 = with a decimating band
+    b->last.aligned = weighted ? 4 : dec ? 5 : wide ? 3 : 2;
     return PFB_OK;
 }
 
@@ -626,8 +699,29 @@ void pfb_bank_destroy(pfb_bank *b) {
         cudaFree(b->hy[i]);
     }
     for (auto &kv : b->tables) free_tables(kv.second);
+    for (cudaStream_t st : b->hs)
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : b->hev)
+        if (e) cudaEventDestroy(e);
     delete b;
 }
+
+int pfb_bank_release_stream(pfb_bank *b, void *stream) {
+    if (!b) return fail(PFB_ERR_INVALID, "pfb_bank_release_stream: null bank");
+    std::lock_guard<std::mutex> lock(b->mu);
+    auto it = b->workspace.find(stream);
+    if (it != b->workspace.end()) {
+        if (it->second.first) {
+            PFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(it->second.first);
+        }
+        b->workspace.erase(it);
+    }
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+long long pfb_device_allocs(void) { return g_device_allocs.load(); }
 
 int pfb_bank_set_warm_tol(pfb_bank *b, double tol) {
     if (!b || !(tol >= 0)) return fail(PFB_ERR_INVALID, "pfb_bank_set_warm_tol: bad argument");
@@ -681,7 +775,7 @@ int pfb_bank_last_launch(const pfb_bank *b, pfb_launch_info *info) {
 
 // pfb_bank_filter with the bank's mutex already held (the TMA path calls it again for the ragged end of a signal)
 static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
-                              int64_t n, int C, int flags, void *stream_);
+                              int64_t n, int C, int flags, void *stream_, FilterExtra *ex = nullptr);
 
 int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
                     int64_t n, int C, int flags, void *stream_) {
@@ -690,13 +784,26 @@ int pfb_bank_filter(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y,
     return bank_filter_locked(b, dtype, x, ldx, y, ldy, states, n, C, flags, stream_);
 }
 
+// A bank's coefficient, transition and scratch tables live on the device it was created on.
+static int check_device(const pfb_bank *b, const char *who) {
+    int dev = -1;
+    PFB_CUDA(cudaGetDevice(&dev));
+    if (dev != b->device)
+        return fail(PFB_ERR_INVALID, "%s: the bank was created on CUDA device %d, the current device is %d", who, b->device, dev);
+    return PFB_OK;
+}
+
+// ex != null: only the fused TMA path is tried -- returns kNotApplicable when the shapes do not fit it, otherwise
+// filters ex->n_done samples (the caller finishes the ragged end).
 static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
-                              int64_t n, int C, int flags, void *stream_) {
+                              int64_t n, int C, int flags, void *stream_, FilterExtra *ex) {
+    if (ex) ex->n_done = 0;
     if (n == 0) {   // nothing to filter: states stay as they are (sosfilt.c loads and stores them unchanged)
         g_status = PFB_OK;
         return PFB_OK;
     }
-    if (!x || !y || !states) return fail(PFB_ERR_INVALID, "pfb_bank_filter: null argument");
+    if (!x || (!y && !(ex && ex->dec && b->B == 1)) || !states) return fail(PFB_ERR_INVALID, "pfb_bank_filter: null argument");
+    if (int rc = check_device(b, "pfb_bank_filter")) return rc;
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad dtype %d", dtype);
     const bool dec = (flags & PFB_DECIMATE2) != 0;
     const int dec_phase = (flags & PFB_DEC_PHASE1) ? 1 : 0;
@@ -735,10 +842,16 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
     // few cascades (many time chunks per cascade) and many cascades (tile rows spread over channels, down to a
     // single chunk per cascade = plain sequential filtering with warp-uniform coefficients and no pre-pass).
     const int tt = 2 * tlen;
-    const bool tma_ok = !(flags & 0x100) && !dec && !exact && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
-                        !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 &&
-                        (ldy * esz) % 16 == 0 && n >= 4LL * tt &&
-                        b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections);
+    bool tma_ok = !(flags & 0x100) && !dec && !exact && !b->per_channel && b->sweeps.size() == 1 && !in_place &&
+                  !env_int("PFB_NO_TMA", 0) && aligned16(x) && aligned16(y) && (ldx * esz) % 16 == 0 &&
+                  (ldy * esz) % 16 == 0 && n >= 4LL * tt &&
+                  b->B * b->K <= (arith64 ? pfb::CoefTable<double>::kMaxSections : pfb::CoefTable<float>::kMaxSections);
+    if (ex) {
+        if (ex->dec) tma_ok = tma_ok && dtype == PFB_F64 && aligned16(ex->y2) && (ex->ldy2 * esz) % 16 == 0;
+        if (ex->wnz) tma_ok = tma_ok && ex->wnz >= 4 && ex->wnz <= 6;
+        if (!tma_ok || (mode != PFB_MODE_AUTO && mode != PFB_MODE_SCAN)) return kNotApplicable;
+        mode = PFB_MODE_SCAN;
+    }
     if (mode == PFB_MODE_AUTO) {
         // enough independent cascades to fill the machine with one lane each -> no time split needed
         const long long lanes_to_fill = (long long)b->sm_count * 16 * 32;
@@ -769,6 +882,8 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         const bool same_arith = dtype == PFB_F64 || !arith64;   // float64 / float64 or float32 / float32
         bool wide = same_arith && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
+        if (ex) wide = false;               // the fused stages live in the 256-byte-fragment kernel
+        if (ex && ex->wnz) J = 1;           // the weighting recurrence is sequential in time: rows are whole channels
         const int ttb = wide ? 2 * tt : tt;
         if (wide) {
             tma_bands(b, &nb, &G, true);
@@ -789,8 +904,13 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         const long long Lt = n / J / ttb * ttb;
         if (Lt >= 4LL * ttb && Lt < 0x7fffffffLL) {
             const long long n_main = Lt * J;
-            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true, wide);
+            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true, wide, ex);
             if (rc) return rc;
+            if (ex) {                // fused stages: the caller finishes the ragged end
+                ex->n_done = n_main;
+                g_status = PFB_OK;
+                return PFB_OK;
+            }
             pfb_launch_info main_info = b->last;
             if (n_main < n) {        // the ragged end continues from the carried states
                 rc = bank_filter_locked(b, dtype, (const char *)x + n_main * esz, ldx, (char *)y + n_main * esz, ldy,
@@ -803,6 +923,7 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
             return PFB_OK;
         }
     }
+    if (ex) return kNotApplicable;
     if (mode == PFB_MODE_SCAN) {
         const long long want_warps = (long long)b->sm_count * 16;
         warps = env_int("PFB_SCAN_WARPS", 0);
@@ -903,17 +1024,16 @@ int pfb_bank_levels_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, dou
     Cg = std::min<long long>(Cg, std::max<long long>(1, (C + 3) / 4));
     void *dx[2] = {nullptr, nullptr}, *ds = nullptr;
     double *dl = nullptr;
-    cudaStream_t sc = nullptr, sh = nullptr;
-    cudaEvent_t in_done[2] = {nullptr, nullptr}, used[2] = {nullptr, nullptr};
+    std::lock_guard<std::mutex> host_lock(b->host_mu);
+    if (int rc0 = check_device(b, "pfb_bank_levels_host")) return rc0;
+    if (int rc0 = b->ensure_host_ctx()) return rc0;
+    cudaStream_t sc = b->hs[0], sh = b->hs[2];
+    cudaEvent_t in_done[2] = {b->hev[0], b->hev[1]}, used[2] = {b->hev[2], b->hev[3]};
     int rc = PFB_OK;
     auto cleanup = [&]() {
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(sh);
         cudaFree(dx[0]); cudaFree(dx[1]); cudaFree(ds); cudaFree(dl);
-        for (int i = 0; i < 2; ++i) {
-            if (in_done[i]) cudaEventDestroy(in_done[i]);
-            if (used[i]) cudaEventDestroy(used[i]);
-        }
-        if (sc) cudaStreamDestroy(sc);
-        if (sh) cudaStreamDestroy(sh);
     };
 #define PFB_CUDA_L(call)                                                                                  \
     do {                                                                                                  \
@@ -924,16 +1044,10 @@ int pfb_bank_levels_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, dou
             return rc;                                                                                    \
         }                                                                                                 \
     } while (0)
-    PFB_CUDA_L(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    PFB_CUDA_L(cudaStreamCreateWithFlags(&sh, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        PFB_CUDA_L(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
-        PFB_CUDA_L(cudaEventCreateWithFlags(&used[i], cudaEventDisableTiming));
-        PFB_CUDA_L(cudaMalloc(&dx[i], (size_t)Cg * pitch * esz));
-    }
+    for (int i = 0; i < 2; ++i) PFB_CUDA_L(counted_malloc(&dx[i], (size_t)Cg * pitch * esz));
     const size_t nstate = (size_t)C * B * b->K * 2;
-    PFB_CUDA_L(cudaMalloc(&ds, nstate * ssz));
-    PFB_CUDA_L(cudaMalloc((void **)&dl, (size_t)C * B * nblocks * sizeof(double)));
+    PFB_CUDA_L(counted_malloc(&ds, nstate * ssz));
+    PFB_CUDA_L(counted_malloc((void **)&dl, (size_t)C * B * nblocks * sizeof(double)));
     PFB_CUDA_L(cudaMemcpyAsync(ds, states, nstate * ssz, cudaMemcpyHostToDevice, sc));
     const int ngroups = (int)((C + Cg - 1) / Cg);
     for (int g = 0; g < ngroups; ++g) {
@@ -974,17 +1088,14 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
     const int B = b->B;
     const long long pitch = (n + 31) / 32 * 32;
     void *dx[2] = {nullptr, nullptr}, *dy[2] = {nullptr, nullptr}, *ds = nullptr;
-    cudaStream_t sc = nullptr, sd = nullptr;
-    cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    if (int rc0 = b->ensure_host_ctx()) return rc0;
+    cudaStream_t sc = b->hs[0], sd = b->hs[1];
+    cudaEvent_t done[2] = {b->hev[0], b->hev[1]}, drained[2] = {b->hev[2], b->hev[3]};
     int rc = PFB_OK;
     auto cleanup = [&]() {
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(sd);
         cudaFree(ds);
-        for (int i = 0; i < 2; ++i) {
-            if (done[i]) cudaEventDestroy(done[i]);
-            if (drained[i]) cudaEventDestroy(drained[i]);
-        }
-        if (sc) cudaStreamDestroy(sc);
-        if (sd) cudaStreamDestroy(sd);
     };
 #define PFB_CUDA_C(call)                                                                                  \
     do {                                                                                                  \
@@ -995,8 +1106,6 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
             return rc;                                                                                    \
         }                                                                                                 \
     } while (0)
-    PFB_CUDA_C(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    PFB_CUDA_C(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
     const int ngroups = (C + Cg - 1) / Cg;
     {   // staging buffers live in the bank: repeated calls (block-wise callers, the bench) do not reallocate
         std::lock_guard<std::mutex> lock(b->mu);
@@ -1010,8 +1119,8 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
             }
             b->hx_bytes = b->hy_bytes = 0;
             for (int i = 0; i < 2; ++i) {
-                PFB_CUDA_C(cudaMalloc(&b->hx[i], need_x));
-                PFB_CUDA_C(cudaMalloc(&b->hy[i], need_y));
+                PFB_CUDA_C(counted_malloc(&b->hx[i], need_x));
+                PFB_CUDA_C(counted_malloc(&b->hy[i], need_y));
             }
             b->hx_bytes = need_x;
             b->hy_bytes = need_y;
@@ -1021,13 +1130,9 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
             dy[i] = b->hy[i];
         }
     }
-    for (int i = 0; i < 2; ++i) {
-        PFB_CUDA_C(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        PFB_CUDA_C(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
-    }
     // all states stay on the device for the whole call (the host array may be pageable: one copy each way)
     const size_t nstate = (size_t)C * B * b->K * 2;
-    PFB_CUDA_C(cudaMalloc(&ds, nstate * ssz));
+    PFB_CUDA_C(counted_malloc(&ds, nstate * ssz));
     PFB_CUDA_C(cudaMemcpyAsync(ds, states, nstate * ssz, cudaMemcpyHostToDevice, sc));
     for (int g = 0; g < ngroups; ++g) {
         const int s = g & 1;
@@ -1087,7 +1192,7 @@ int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *
     double *partial = levels;
     long long pld = ld_levels;
     if (r > 1) {
-        PFB_CUDA(cudaMallocAsync((void **)&partial, (size_t)Q * nunits * sizeof(double), stream));
+        PFB_CUDA(counted_malloc_async((void **)&partial, (size_t)Q * nunits * sizeof(double), stream));
         pld = nunits;
     }
     int nb, G;
@@ -1133,6 +1238,8 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: bad dtype");
     if (n < 0 || C <= 0 || ldx < n || ldy < n) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: bad sizes");
     if (flags & PFB_DECIMATE2) return fail(PFB_ERR_INVALID, "pfb_bank_filter_host: PFB_DECIMATE2 is a device-pointer option");
+    std::lock_guard<std::mutex> host_lock(b->host_mu);
+    if (int rc0 = check_device(b, "pfb_bank_filter_host")) return rc0;
     const size_t esz = dtype == PFB_F64 ? 8 : 4;
     const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
     const long long Q = (long long)C * b->B;
@@ -1159,21 +1266,17 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
     const long long pitch = (nb + 31) / 32 * 32;
 
     void *dx = nullptr, *dy[2] = {nullptr, nullptr}, *ds = nullptr;
-    cudaStream_t sc = nullptr, sd = nullptr;
-    cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr}, xin[2] = {nullptr, nullptr};
+    if (int rc0 = b->ensure_host_ctx()) return rc0;
+    cudaStream_t sc = b->hs[0], sd = b->hs[1];
+    cudaEvent_t done[2] = {b->hev[0], b->hev[1]}, drained[2] = {b->hev[2], b->hev[3]};
     int rc = PFB_OK;
     auto cleanup = [&]() {
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(sd);
         cudaFree(dx);
         cudaFree(dy[0]);
         cudaFree(dy[1]);
         cudaFree(ds);
-        for (int i = 0; i < 2; ++i) {
-            if (done[i]) cudaEventDestroy(done[i]);
-            if (drained[i]) cudaEventDestroy(drained[i]);
-            if (xin[i]) cudaEventDestroy(xin[i]);
-        }
-        if (sc) cudaStreamDestroy(sc);
-        if (sd) cudaStreamDestroy(sd);
     };
 #define PFB_CUDA_H(call)                                                                                  \
     do {                                                                                                  \
@@ -1184,18 +1287,11 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
             return rc;                                                                                    \
         }                                                                                                 \
     } while (0)
-    PFB_CUDA_H(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-    PFB_CUDA_H(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        PFB_CUDA_H(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-        PFB_CUDA_H(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
-        PFB_CUDA_H(cudaEventCreateWithFlags(&xin[i], cudaEventDisableTiming));
-    }
     // two input blocks [C][pitch] and two output blocks [Q][pitch]
-    PFB_CUDA_H(cudaMalloc(&dx, 2 * (size_t)C * pitch * esz));
-    PFB_CUDA_H(cudaMalloc(&dy[0], (size_t)Q * pitch * esz));
-    if (n > nb) PFB_CUDA_H(cudaMalloc(&dy[1], (size_t)Q * pitch * esz));
-    PFB_CUDA_H(cudaMalloc(&ds, nstate * ssz));
+    PFB_CUDA_H(counted_malloc(&dx, 2 * (size_t)C * pitch * esz));
+    PFB_CUDA_H(counted_malloc(&dy[0], (size_t)Q * pitch * esz));
+    if (n > nb) PFB_CUDA_H(counted_malloc(&dy[1], (size_t)Q * pitch * esz));
+    PFB_CUDA_H(counted_malloc(&ds, nstate * ssz));
     PFB_CUDA_H(cudaMemcpyAsync(ds, states, nstate * ssz, cudaMemcpyHostToDevice, sc));
 
     const long long nblocks = n == 0 ? 0 : (n + nb - 1) / nb;
@@ -1226,6 +1322,423 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
     g_status = PFB_OK;
     return PFB_OK;
 #undef PFB_CUDA_H
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weighted bank: SPL-weighting prefilter (splweighting.py:61-80) + bank (octbank.py:412-434) as ONE call.
+// ------------------------------------------------------------------------------------------------
+int pfb_bank_filter_weighted(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,
+                             const double *wb, int nwb, const double *wa, int nwa, double *wz, int64_t n, int C, int flags,
+                             void *stream_) {
+    if (!b) return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: null bank");
+    if (n == 0) {
+        g_status = PFB_OK;
+        return PFB_OK;
+    }
+    if (!x || !y || !states || !wb || !wa || !wz || nwb < 1 || nwa < 1 || nwb > 8 || nwa > 8 || C <= 0 || n < 0 || ldx < n)
+        return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: bad argument (at most 8 taps)");
+    if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: bad dtype %d", dtype);
+    if (wa[0] == 0.0) return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: a[0] must not be 0");
+    if (flags & (PFB_DECIMATE2 | PFB_DEC_PHASE1)) return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: no decimation here");
+    if ((const void *)x == (const void *)y) return fail(PFB_ERR_INVALID, "pfb_bank_filter_weighted: x must not alias y");
+    std::lock_guard<std::mutex> lock(b->mu);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int ntaps = std::max(nwb, nwa), nz = std::max(ntaps - 1, 1);
+    const size_t esz = dtype == PFB_F64 ? 8 : 4;
+    FilterExtra ex;
+    for (int k = 0; k < 8; ++k) {   // scipy normalises by a[0] first
+        ex.wb[k] = k < nwb ? wb[k] / wa[0] : 0.0;
+        ex.wa[k] = k < nwa ? wa[k] / wa[0] : 0.0;
+    }
+    ex.wnz = nz;
+    ex.wz = wz;
+    // Fused pass: one chunk per cascade, so it pays when (channel blocks x band groups) fill a good part of the
+    // machine; few channels take the weighting kernel and the time-chunked bank.  PFB_WEIGHT_FUSED=0/1 overrides.
+    int nbw, G;
+    tma_bands(b, &nbw, &G, false);
+    bool fused = !(flags & PFB_EXACT) && nz >= 4 && nz <= 6 && (long long)((C + 31) / 32) * G * 2 >= b->sm_count;
+    fused = env_int("PFB_WEIGHT_FUSED", fused ? 1 : 0) != 0;
+    long long done = 0;
+    int kernels = 0;
+    pfb_launch_info fused_info{};
+    if (fused) {
+        int rc = bank_filter_locked(b, dtype, x, ldx, y, ldy, states, n, C, flags, stream_, &ex);
+        if (rc < 0) return rc;
+        if (rc == PFB_OK) {
+            done = ex.n_done;
+            kernels += b->last.kernels;
+            fused_info = b->last;
+        }
+    }
+    if (done < n) {   // unfused (remainder of the) signal: weighting kernel into a scratch row set, then the bank
+        const long long rem = n - done;
+        const long long pitch = (rem + 31) / 32 * 32;
+        void *tmp = nullptr;
+        PFB_CUDA(counted_malloc_async(&tmp, (size_t)C * pitch * esz, stream));
+        pfb::TfParams tp{};
+        tp.x = (const char *)x + done * esz, tp.y = tmp, tp.z = wz;
+        tp.n = rem, tp.ldx = ldx, tp.ldy = pitch, tp.R = C, tp.ntaps = ntaps;
+        for (int k = 0; k < 8; ++k) tp.b[k] = ex.wb[k], tp.a[k] = ex.wa[k];
+        const bool al = aligned16(tp.x) && (ldx * esz) % 16 == 0;
+        int err = pfb::launch_tf(tp, dtype, al, stream);
+        int rc = PFB_OK;
+        if (err) rc = fail(PFB_ERR_CUDA, "weighting kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+        ++kernels;
+        if (!rc) rc = bank_filter_locked(b, dtype, tmp, pitch, (char *)y + done * esz, ldy, states, rem, C, flags, stream_);
+        cudaFreeAsync(tmp, stream);
+        if (rc) return rc;
+        kernels += b->last.kernels;
+    }
+    if (done > 0) b->last = fused_info;
+    b->last.kernels = kernels;
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decimating band path as one call: stage m runs at fs / 2^m; every stage's bands and the anti-alias
+// low-pass that feeds the next stage are filtered in ONE pass over the stage signal (the anti-alias
+// cascade is one more band warp whose output is stored decimated), so no band signal is ever written
+// at a rate above its own and the Python loop over stages is gone.
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct pfb_decbank {
+    int device = 0;
+    int M = 0;                         // halving stages; stages 0 .. M
+    int K = 0, Kaa = 0, Kp = 0;        // band sections, anti-alias sections, sections of the padded anti-alias cascade
+    bool fusable = false;              // Kp == K: the anti-alias cascade fits the bands' kernel as one more band
+    std::vector<int> nb;               // bands per stage
+    std::vector<pfb_bank *> fused;     // stage m < M: bands + anti-alias cascade (nb[m] + 1 rows), or null
+    std::vector<pfb_bank *> bands;     // stage m: nb[m] rows, or null when the stage has no band
+    pfb_bank *aa = nullptr;            // the anti-alias cascade alone (1 row, Kp sections)
+    void *sig[2] = {nullptr, nullptr}; // stage signals (ping-pong): stage m reads sig[m & 1] (m > 0), writes sig[(m + 1) & 1]
+    size_t sig_bytes[2] = {0, 0};
+    std::mutex mu;
+    int last_kernels = 0, last_fused = 0;
+};
+
+extern "C" {
+
+void pfb_decbank_destroy(pfb_decbank *d) {
+    if (!d) return;
+    for (pfb_bank *b : d->fused) pfb_bank_destroy(b);
+    for (pfb_bank *b : d->bands) pfb_bank_destroy(b);
+    pfb_bank_destroy(d->aa);
+    cudaFree(d->sig[0]);
+    cudaFree(d->sig[1]);
+    delete d;
+}
+
+int pfb_decbank_create(pfb_decbank **out, int nstages, const int *bands_per_stage, const double *const *sos_per_stage, int K,
+                       const double *aa_sos, int Kaa) {
+    if (!out || nstages < 1 || !bands_per_stage || !sos_per_stage || K <= 0 || (nstages > 1 && (!aa_sos || Kaa <= 0)))
+        return fail(PFB_ERR_INVALID, "pfb_decbank_create: bad arguments");
+    pfb_decbank *d = new pfb_decbank;
+    d->M = nstages - 1;
+    d->K = K;
+    d->Kaa = nstages > 1 ? Kaa : 0;
+    // the decimating store needs a cascade that runs in one sweep: pad to the next sweep size
+    int Kp = std::max(K, d->Kaa);
+    static const int sizes[] = {1, 2, 3, 4, 6, 8};
+    for (int sz : sizes)
+        if (sz >= Kp) { Kp = sz; break; }
+    if (d->M > 0 && Kp > 8) {
+        delete d;
+        return fail(PFB_ERR_INVALID, "pfb_decbank_create: cascades of more than 8 sections cannot decimate");
+    }
+    d->Kp = Kp;
+    d->fusable = d->M > 0 && Kp == K;
+    d->nb.assign(bands_per_stage, bands_per_stage + nstages);
+    // anti-alias cascade padded with identity sections (b0 = 1: they pass their input through unchanged)
+    std::vector<double> aap((size_t)Kp * 6, 0.0);
+    for (int k = 0; k < Kp; ++k) {
+        if (k < d->Kaa) std::copy(aa_sos + 6 * k, aa_sos + 6 * k + 6, &aap[6 * k]);
+        else aap[6 * k] = 1.0, aap[6 * k + 3] = 1.0;
+    }
+    int rc = PFB_OK;
+    PFB_CUDA(cudaGetDevice(&d->device));
+    if (d->M > 0) rc = pfb_bank_create(&d->aa, aap.data(), 1, 1, Kp, 0);
+    d->fused.assign(nstages, nullptr);
+    d->bands.assign(nstages, nullptr);
+    for (int m = 0; m < nstages && rc == PFB_OK; ++m) {
+        const int B = d->nb[m];
+        if (B < 0 || (B > 0 && !sos_per_stage[m])) rc = fail(PFB_ERR_INVALID, "pfb_decbank_create: stage %d has no coefficients", m);
+        if (rc == PFB_OK && B > 0) rc = pfb_bank_create(&d->bands[m], sos_per_stage[m], 1, B, K, 0);
+        if (rc == PFB_OK && m < d->M && d->fusable) {
+            std::vector<double> f((size_t)(B + 1) * K * 6);
+            if (B > 0) std::copy(sos_per_stage[m], sos_per_stage[m] + (size_t)B * K * 6, f.begin());
+            std::copy(aap.begin(), aap.end(), f.begin() + (size_t)B * K * 6);
+            rc = pfb_bank_create(&d->fused[m], f.data(), 1, B + 1, K, 0);
+        }
+    }
+    if (rc != PFB_OK) {
+        pfb_decbank_destroy(d);
+        return rc;
+    }
+    *out = d;
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_decbank_info(const pfb_decbank *d, int *stages, int *aa_sections_padded, int *last_kernels, int *last_fused_stages) {
+    if (!d) return fail(PFB_ERR_INVALID, "pfb_decbank_info: null argument");
+    if (stages) *stages = d->M + 1;
+    if (aa_sections_padded) *aa_sections_padded = d->Kp;
+    if (last_kernels) *last_kernels = d->last_kernels;
+    if (last_fused_stages) *last_fused_stages = d->last_fused;
+    return PFB_OK;
+}
+
+int pfb_decbank_filter(pfb_decbank *d, const double *x, int64_t ldx, void *const *y, const int64_t *ldy,
+                       void *const *band_states, double *aa_states, int *phases, int64_t n, int C, int flags, void *stream_) {
+    if (!d || !x || !y || !ldy || !band_states || (d->M > 0 && (!aa_states || !phases)) || n < 0 || C <= 0 || ldx < n)
+        return fail(PFB_ERR_INVALID, "pfb_decbank_filter: bad argument");
+    if (flags & (PFB_DECIMATE2 | PFB_DEC_PHASE1 | PFB_ARITH_F64))
+        return fail(PFB_ERR_INVALID, "pfb_decbank_filter: flags may only select the mode and PFB_EXACT");
+    std::lock_guard<std::mutex> lock(d->mu);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = -1;
+    PFB_CUDA(cudaGetDevice(&dev));
+    if (dev != d->device) return fail(PFB_ERR_INVALID, "pfb_decbank_filter: created on device %d, current device is %d", d->device, dev);
+    // stage signal buffers: stage m + 1 holds at most ceil(n_m / 2) samples per channel
+    {
+        long long nm = n;
+        size_t need[2] = {0, 0};
+        for (int m = 0; m < d->M; ++m) {
+            nm = (nm + 1) / 2;
+            const long long pitch = (nm + 31) / 32 * 32;
+            need[(m + 1) & 1] = std::max<size_t>(need[(m + 1) & 1], (size_t)C * (size_t)pitch * sizeof(double));
+        }
+        for (int i = 0; i < 2; ++i)
+            if (d->sig_bytes[i] < need[i]) {
+                if (d->sig[i]) {
+                    PFB_CUDA(cudaDeviceSynchronize());
+                    cudaFree(d->sig[i]);
+                    d->sig[i] = nullptr;
+                    d->sig_bytes[i] = 0;
+                }
+                PFB_CUDA(counted_malloc(&d->sig[i], need[i]));
+                d->sig_bytes[i] = need[i];
+            }
+    }
+    const bool exact = (flags & PFB_EXACT) != 0;
+    const bool try_fused = d->fusable && !exact && !env_int("PFB_DEC_UNFUSED", 0);
+    d->last_kernels = d->last_fused = 0;
+    const double *in = x;
+    long long ld_in = ldx, nm = n;
+    for (int m = 0; m <= d->M && nm > 0; ++m) {
+        const int B = d->nb[m];
+        if (B > 0 && (!y[m] || !band_states[m] || ldy[m] < nm))
+            return fail(PFB_ERR_INVALID, "pfb_decbank_filter: stage %d needs an output of %lld samples per row", m, nm);
+        if (m == d->M) {
+            if (B > 0) {
+                int rc = pfb_bank_filter(d->bands[m], PFB_F64, in, ld_in, y[m], ldy[m], band_states[m], nm, C, flags, stream_);
+                if (rc) return rc;
+                d->last_kernels += d->bands[m]->last.kernels;
+            }
+            break;
+        }
+        const int ph = phases[m] & 1;
+        const long long n_next = (nm - ph + 1) / 2;
+        const long long pitch2 = ((nm + 1) / 2 + 31) / 32 * 32;
+        double *out2 = (double *)d->sig[(m + 1) & 1];
+        double *aast = aa_states + (size_t)m * C * d->Kp * 2;
+        long long done = 0;
+        if (try_fused) {
+            FilterExtra ex;
+            ex.dec = true, ex.dec_phase = ph, ex.y2 = out2, ex.ldy2 = pitch2, ex.dec_states = aast;
+            pfb_bank *fb = d->fused[m];
+            std::lock_guard<std::mutex> block(fb->mu);
+            int rc = bank_filter_locked(fb, PFB_F64, in, ld_in, B > 0 ? y[m] : nullptr, B > 0 ? ldy[m] : (nm + 31) / 32 * 32,
+                                        B > 0 ? band_states[m] : (void *)aast, nm, C, flags, stream_, &ex);
+            if (rc < 0) return rc;
+            if (rc == PFB_OK && ex.n_done > 0) {
+                done = ex.n_done;
+                d->last_kernels += fb->last.kernels;
+                ++d->last_fused;
+            }
+        }
+        if (done < nm) {   // (ragged end of) the stage: bands and the anti-alias cascade as separate passes
+            const long long rem = nm - done;
+            if (B > 0) {
+                int rc = pfb_bank_filter(d->bands[m], PFB_F64, in + done, ld_in, (double *)y[m] + done, ldy[m], band_states[m], rem, C,
+                                         flags, stream_);
+                if (rc) return rc;
+                d->last_kernels += d->bands[m]->last.kernels;
+            }
+            // `done` is even, so the remainder starts on the decimator phase of the block and its kept samples
+            // continue at output index done / 2
+            int rc = pfb_bank_filter(d->aa, PFB_F64, in + done, ld_in, out2 + done / 2, pitch2, aast, rem, C,
+                                     flags | PFB_DECIMATE2 | (ph ? PFB_DEC_PHASE1 : 0), stream_);
+            if (rc) return rc;
+            d->last_kernels += d->aa->last.kernels;
+        }
+        phases[m] = (int)((ph + nm) & 1);
+        in = out2;
+        ld_in = pitch2;
+        nm = n_next;
+    }
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming session: block-wise filtering of HOST audio with device-resident states (the reason the
+// reference's filter functions carry states: blockprocessing.py:3-72, sosfiltering.py:143-147).
+// Streams, events and staging slots are created once; pushing a block enqueues H2D, kernels and D2H
+// and returns; nothing is allocated after the first block of a given length.
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct pfb_stream {
+    pfb_bank *bank = nullptr;
+    int device = 0, dtype = PFB_F64, C = 0, flags = 0;
+    long long max_block = 0, pitch = 0;
+    size_t esz = 8, ssz = 8;
+    cudaStream_t sh = nullptr, sc = nullptr, sd = nullptr;      // input copies, kernels, output copies
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    void *dx[2] = {nullptr, nullptr}, *dy[2] = {nullptr, nullptr}, *ds = nullptr;
+    long long blocks = 0, samples = 0;
+    long long allocs_at_create = 0, allocs_after_first = -1;
+    std::mutex mu;
+};
+
+extern "C" {
+
+void pfb_stream_destroy(pfb_stream *s) {
+    if (!s) return;
+    if (s->sc) {
+        cudaStreamSynchronize(s->sh);
+        cudaStreamSynchronize(s->sc);
+        cudaStreamSynchronize(s->sd);
+        pfb_bank_release_stream(s->bank, (void *)s->sc);      // the bank's per-stream scratch goes with the stream
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->dx[i]);
+        cudaFree(s->dy[i]);
+        if (s->in_done[i]) cudaEventDestroy(s->in_done[i]);
+        if (s->done[i]) cudaEventDestroy(s->done[i]);
+        if (s->drained[i]) cudaEventDestroy(s->drained[i]);
+    }
+    cudaFree(s->ds);
+    if (s->sh) cudaStreamDestroy(s->sh);
+    if (s->sc) cudaStreamDestroy(s->sc);
+    if (s->sd) cudaStreamDestroy(s->sd);
+    delete s;
+}
+
+int pfb_stream_create(pfb_stream **out, pfb_bank *bank, int dtype, int C, int64_t max_block, int flags) {
+    if (!out || !bank || C <= 0 || max_block <= 0 || (dtype != PFB_F32 && dtype != PFB_F64))
+        return fail(PFB_ERR_INVALID, "pfb_stream_create: bad arguments");
+    if (flags & (PFB_DECIMATE2 | PFB_DEC_PHASE1)) return fail(PFB_ERR_INVALID, "pfb_stream_create: no decimation here");
+    if (bank->per_channel && C != bank->C_sos) return fail(PFB_ERR_INVALID, "pfb_stream_create: bank holds %d channels", bank->C_sos);
+    if (int rc = check_device(bank, "pfb_stream_create")) return rc;
+    pfb_stream *s = new pfb_stream;
+    s->bank = bank;
+    s->device = bank->device;
+    s->dtype = dtype, s->C = C, s->flags = flags;
+    s->max_block = max_block;
+    s->pitch = (max_block + 31) / 32 * 32;
+    s->esz = dtype == PFB_F64 ? 8 : 4;
+    s->ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
+    s->allocs_at_create = g_device_allocs.load();
+    const size_t Q = (size_t)C * bank->B;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->sh, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->sc, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->sd, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&s->in_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->drained[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = counted_malloc(&s->dx[i], (size_t)C * s->pitch * s->esz);
+        if (e == cudaSuccess) e = counted_malloc(&s->dy[i], Q * s->pitch * s->esz);
+    }
+    const size_t state_bytes = Q * bank->K * 2 * s->ssz;
+    if (e == cudaSuccess) e = counted_malloc(&s->ds, state_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->ds, 0, state_bytes, s->sc);
+    if (e != cudaSuccess) {
+        pfb_stream_destroy(s);
+        return fail(PFB_ERR_CUDA, "pfb_stream_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_stream_push(pfb_stream *s, const void *x, int64_t ldx, void *y, int64_t ldy, int64_t n) {
+    if (!s || !x || !y || n < 0 || n > s->max_block || ldx < n || ldy < n)
+        return fail(PFB_ERR_INVALID, "pfb_stream_push: bad argument (block of at most %lld samples)", s ? s->max_block : 0LL);
+    if (n == 0) {
+        g_status = PFB_OK;
+        return PFB_OK;
+    }
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (int rc = check_device(s->bank, "pfb_stream_push")) return rc;
+    const int slot = (int)(s->blocks & 1);
+    const size_t esz = s->esz, Q = (size_t)s->C * s->bank->B;
+    // the slot's previous block (two pushes ago) must have left the device before its buffers are reused
+    if (s->blocks >= 2) PFB_CUDA(cudaStreamWaitEvent(s->sh, s->drained[slot], 0));
+    PFB_CUDA(cudaMemcpy2DAsync(s->dx[slot], s->pitch * esz, x, ldx * esz, n * esz, (size_t)s->C, cudaMemcpyHostToDevice, s->sh));
+    PFB_CUDA(cudaEventRecord(s->in_done[slot], s->sh));
+    PFB_CUDA(cudaStreamWaitEvent(s->sc, s->in_done[slot], 0));
+    if (s->blocks >= 2) PFB_CUDA(cudaStreamWaitEvent(s->sc, s->drained[slot], 0));
+    int rc = pfb_bank_filter(s->bank, s->dtype, s->dx[slot], s->pitch, s->dy[slot], s->pitch, s->ds, n, s->C, s->flags, (void *)s->sc);
+    if (rc) return rc;
+    PFB_CUDA(cudaEventRecord(s->done[slot], s->sc));
+    PFB_CUDA(cudaStreamWaitEvent(s->sd, s->done[slot], 0));
+    PFB_CUDA(cudaMemcpy2DAsync(y, ldy * esz, s->dy[slot], s->pitch * esz, n * esz, Q, cudaMemcpyDeviceToHost, s->sd));
+    PFB_CUDA(cudaEventRecord(s->drained[slot], s->sd));
+    ++s->blocks;
+    s->samples += n;
+    if (s->allocs_after_first < 0) s->allocs_after_first = g_device_allocs.load();
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_stream_sync(pfb_stream *s) {
+    if (!s) return fail(PFB_ERR_INVALID, "pfb_stream_sync: null session");
+    PFB_CUDA(cudaStreamSynchronize(s->sh));
+    PFB_CUDA(cudaStreamSynchronize(s->sc));
+    PFB_CUDA(cudaStreamSynchronize(s->sd));
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_stream_wait(pfb_stream *s, int64_t block) {
+    if (!s || block < 0) return fail(PFB_ERR_INVALID, "pfb_stream_wait: bad argument");
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(s->mu);
+        if (block >= s->blocks) return fail(PFB_ERR_INVALID, "pfb_stream_wait: block %lld has not been pushed", (long long)block);
+        // the slot's event belongs to the latest block of the same parity: waiting for it also covers `block`
+        ev = s->drained[block & 1];
+    }
+    PFB_CUDA(cudaEventSynchronize(ev));
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_stream_states(pfb_stream *s, void *states_host, int set) {
+    if (!s || !states_host) return fail(PFB_ERR_INVALID, "pfb_stream_states: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    const size_t bytes = (size_t)s->C * s->bank->B * s->bank->K * 2 * s->ssz;
+    if (set) PFB_CUDA(cudaMemcpyAsync(s->ds, states_host, bytes, cudaMemcpyHostToDevice, s->sc));
+    else PFB_CUDA(cudaMemcpyAsync(states_host, s->ds, bytes, cudaMemcpyDeviceToHost, s->sc));
+    PFB_CUDA(cudaStreamSynchronize(s->sc));
+    g_status = PFB_OK;
+    return PFB_OK;
+}
+
+int pfb_stream_stats(pfb_stream *s, pfb_stream_info *info) {
+    if (!s || !info) return fail(PFB_ERR_INVALID, "pfb_stream_stats: null argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    info->blocks = s->blocks;
+    info->samples = s->samples;
+    const long long now = g_device_allocs.load();
+    info->device_allocs_total = now - s->allocs_at_create;
+    info->device_allocs_after_first_block = s->allocs_after_first < 0 ? 0 : now - s->allocs_after_first;
+    return PFB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

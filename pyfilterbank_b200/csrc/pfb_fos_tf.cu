@@ -23,6 +23,7 @@
 
 #include "pfb_kernels.cuh"
 #include "pfb_fos_tma.cuh"
+#include "pfb_tf.cuh"
 #include "../../include/pfb_sos.h"
 
 namespace pfb {
@@ -122,36 +123,17 @@ __global__ void __launch_bounds__(128, 3) fos_seq_kernel(const FosParams p) {
     }
 }
 
-struct TfParams {
-    const double *x;
-    double *y;
-    double *z;            // [R][ntaps-1] in/out
-    long long n, ldx, ldy;
-    int R, ntaps;
-    double b[8], a[8];    // a[0] == 1 (normalised on the host like scipy does)
-};
-
-// One scipy _linear_filter step (direct form II transposed, a[0] == 1), every product and sum rounded separately
-// in scipy's order: the weighting filters have a 4-fold zero at z = 1, so FMA contraction alone moves the
-// result by ~1e-9 relative.   y = z0 + b0 x ; z[k] = (z[k+1] + x b[k+1]) - y a[k+1] ; z[NZ-1] = x b[NZ] - y a[NZ]
-template <int NZ>
-__device__ __forceinline__ double tf_step(double xi, const double (&b)[8], const double (&a)[8], double (&z)[NZ]) {
-    const double yi = __dadd_rn(z[0], __dmul_rn(b[0], xi));
-#pragma unroll
-    for (int k = 0; k < NZ - 1; ++k)
-        z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(xi, b[k + 1])), __dmul_rn(yi, a[k + 1]));
-    z[NZ - 1] = __dsub_rn(__dmul_rn(xi, b[NZ]), __dmul_rn(yi, a[NZ]));
-    return yi;
-}
-
 // One lane per row, one warp per CTA.  Measured (scripts/tf_time.py): a warp needs ~94 clocks per sample for the
-// 25 separately rounded FP64 operations of the 7-tap filter, and two rows per lane take exactly twice as long, so
-// the limit is the single-warp FP64 issue rate, not the dependent chain; rows are therefore spread over as many SM
-// sub-partitions as possible (one warp each).  NZ = taps - 1 delay values.
-template <int NZ, bool ALIGNED, int kTfStages>
+// 25 separately rounded FP64 operations of the 7-tap filter (57 of them arithmetic, the rest tile loads and stores:
+// scripts/sass_sched.py), and two rows per lane take exactly twice as long, so the limit is the single-warp issue
+// rate, not the dependent chain; rows are therefore spread over as many SM sub-partitions as possible (one warp
+// each).  NZ = taps - 1 delay values.  T: float64 rows, or float32 rows filtered in float64 arithmetic.
+template <typename T, int NZ, bool ALIGNED, int kTfStages>
 __global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfParams p) {
     extern __shared__ __align__(128) char smem[];
-    constexpr int TLEN = 16;
+    using V = typename Vec16<T>::type;
+    constexpr int EPV = Vec16<T>::N;
+    constexpr int TLEN = kRowBytes / (int)sizeof(T);
     const int lane = threadIdx.x & 31, key = lane & 7;
     char *buf0 = smem;
     const long long r0 = (long long)blockIdx.x * 32;
@@ -166,9 +148,10 @@ __global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfPa
     double b[8], a[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { b[k] = p.b[k]; a[k] = p.a[k]; }
-    const double *xrow = p.x + (active ? r : 0) * p.ldx;
+    const T *xbase = reinterpret_cast<const T *>(p.x);
+    const T *xrow = xbase + (active ? r : 0) * p.ldx;
     const long long mylen = active ? n : 0;
-    CoopIO<double, ALIGNED> io(p.x, p.y + r0 * p.ldy, 0, p.ldy, lane);
+    CoopIO<T, ALIGNED> io(xbase, reinterpret_cast<T *>(p.y) + r0 * p.ldy, 0, p.ldy, lane);
     auto rowlen = [=](int row) -> long long { return (r0 + row < R) ? n : 0; };
     char *myrow = buf0 + lane * kRowBytes;
     const bool warp_full = r0 + 32 <= R;
@@ -176,33 +159,35 @@ __global__ void __launch_bounds__(32) tf_seq_kernel(const __grid_constant__ TfPa
     // kTfStages tiles in flight: one tile is only ~16 x 50 clocks of arithmetic, less than a DRAM round trip
 #pragma unroll
     for (int t = 0; t < kTfStages - 1; ++t) {
-        if (t < nt) load_row_own<double, ALIGNED>(myrow + t * kTileBytes, key, xrow, mylen, (long long)t * TLEN, p.x);
+        if (t < nt) load_row_own<T, ALIGNED>(myrow + t * kTileBytes, key, xrow, mylen, (long long)t * TLEN, xbase);
         cp_async_commit();
     }
     for (long long t = 0; t < nt; ++t) {
         const int cb = (int)(t % kTfStages);
         if (t + kTfStages - 1 < nt)
-            load_row_own<double, ALIGNED>(myrow + (int)((t + kTfStages - 1) % kTfStages) * kTileBytes, key, xrow, mylen,
-                                          (t + kTfStages - 1) * TLEN, p.x);
+            load_row_own<T, ALIGNED>(myrow + (int)((t + kTfStages - 1) % kTfStages) * kTileBytes, key, xrow, mylen,
+                                     (t + kTfStages - 1) * TLEN, xbase);
         cp_async_commit();
         cp_async_wait<kTfStages - 1>();
         const int valid = clamp_i(mylen - t * TLEN, TLEN);
         char *row = myrow + cb * kTileBytes;
         if (valid == TLEN) {   // whole tile: registers in, registers out, no per-sample predicates
-            double2 v[8];
+            V v[kVecPerRow];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const double2 *>(row + ((i ^ key) << 4));
+            for (int i = 0; i < kVecPerRow; ++i) v[i] = *reinterpret_cast<const V *>(row + ((i ^ key) << 4));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i].x = tf_step<NZ>(v[i].x, b, a, z);
-                v[i].y = tf_step<NZ>(v[i].y, b, a, z);
+            for (int i = 0; i < kVecPerRow; ++i) {
+                T *e = reinterpret_cast<T *>(&v[i]);
+#pragma unroll
+                for (int j = 0; j < EPV; ++j) e[j] = (T)tf_step<NZ>((double)e[j], b, a, z);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<double2 *>(row + ((i ^ key) << 4)) = v[i];
+            for (int i = 0; i < kVecPerRow; ++i) *reinterpret_cast<V *>(row + ((i ^ key) << 4)) = v[i];
         } else {
             for (int i = 0; i < valid; ++i) {
-                double *e = reinterpret_cast<double *>(row + (((i >> 1) ^ key) << 4) + (i & 1) * 8);
-                *e = tf_step<NZ>(*e, b, a, z);
+                const int byte = i * (int)sizeof(T);
+                T *e = reinterpret_cast<T *>(row + (((byte >> 4) ^ key) << 4) + (byte & 15));
+                *e = (T)tf_step<NZ>((double)*e, b, a, z);
             }
         }
         __syncwarp();
@@ -246,27 +231,32 @@ int launch_fos(const FosParams &p, int order, bool aligned, cudaStream_t s) {
     }
 }
 
-template <int NZ>
+template <typename T, int NZ>
 static int run_tf(const TfParams &p, bool aligned, cudaStream_t s) {
     // two tiles in flight (deeper rings measured slower: 12.5 / 18.2 / 19.2 ms for 2 / 3 / 4 stages on 1024 rows x 240 k)
     const unsigned grid = (unsigned)((p.R + 31) / 32);
-    if (aligned) tf_seq_kernel<NZ, true, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
-    else tf_seq_kernel<NZ, false, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
+    if (aligned) tf_seq_kernel<T, NZ, true, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
+    else tf_seq_kernel<T, NZ, false, 2><<<grid, 32, 2 * kTileBytes, s>>>(p);
     return (int)cudaGetLastError();
 }
 
-int launch_tf(const TfParams &p, bool aligned, cudaStream_t s) {
+template <typename T>
+static int launch_tf_t(const TfParams &p, bool aligned, cudaStream_t s) {
     switch (p.ntaps - 1) {
         case 0:   // pure gain: one (always zero) delay value keeps the state layout [R][max(taps - 1, 1)]
-        case 1: return run_tf<1>(p, aligned, s);
-        case 2: return run_tf<2>(p, aligned, s);
-        case 3: return run_tf<3>(p, aligned, s);
-        case 4: return run_tf<4>(p, aligned, s);
-        case 5: return run_tf<5>(p, aligned, s);
-        case 6: return run_tf<6>(p, aligned, s);
-        case 7: return run_tf<7>(p, aligned, s);
+        case 1: return run_tf<T, 1>(p, aligned, s);
+        case 2: return run_tf<T, 2>(p, aligned, s);
+        case 3: return run_tf<T, 3>(p, aligned, s);
+        case 4: return run_tf<T, 4>(p, aligned, s);
+        case 5: return run_tf<T, 5>(p, aligned, s);
+        case 6: return run_tf<T, 6>(p, aligned, s);
+        case 7: return run_tf<T, 7>(p, aligned, s);
         default: return (int)cudaErrorInvalidValue;
     }
+}
+
+int launch_tf(const TfParams &p, int dtype, bool aligned, cudaStream_t s) {
+    return dtype == PFB_F64 ? launch_tf_t<double>(p, aligned, s) : launch_tf_t<float>(p, aligned, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -601,7 +591,7 @@ int pfb_tf_filter_f64(const double *x, int64_t ldx, double *y, int64_t ldy, cons
         p.a[k] = k < na ? a[k] / a[0] : 0.0;
     }
     const bool aligned = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (ldx * 8) % 16 == 0 && (ldy * 8) % 16 == 0;
-    int err = pfb::launch_tf(p, aligned, (cudaStream_t)stream);
+    int err = pfb::launch_tf(p, PFB_F64, aligned, (cudaStream_t)stream);
     if (err) return pfb_set_error(PFB_ERR_CUDA, cudaGetErrorString((cudaError_t)err));
     return pfb_set_error(PFB_OK, "");
 }

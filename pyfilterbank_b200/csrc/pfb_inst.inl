@@ -61,16 +61,18 @@ static int run_scan(const SosParams &p, int warps, const double *coef_host, int 
 
 template <int K, int NBMAX, bool SCALED>
 static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                      cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+                      const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
     auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, 0, NBMAX, SCALED>;
     auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED>;
     auto kern_l = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED>;
-    const int smem_a = kTmaStages * 2 * kTileBytes + 2 * kTmaStages * 8;
-    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 2 * kTmaStages * 8;
+    const int smem_a = kTmaStages * 2 * kTileBytes + 3 * kTmaStages * 8;
+    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 3 * kTmaStages * 8;
     cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e != cudaSuccess) return (int)e;
+    if (p.weighted && (NBMAX != kTmaSmallBands || p.J != 1 || p.wide)) return (int)cudaErrorInvalidValue;
+    if (p.dec_band1 && (!PFB_HAS_DEC || p.levels || p.wide || p.weighted)) return (int)cudaErrorInvalidValue;
     static thread_local CoefTable<PFB_A> tab;
     for (int r = 0; r < p.B; ++r) {
         double total_gain = 1.0;
@@ -102,7 +104,7 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             if (e != cudaSuccess) return (int)e;
             kern_h<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, xmap);
         } else
-            kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap);
+            kern_a<<<grid_a, (p.nb_a + 1) * 32, smem_a, s>>>(p, tab, xmap, ymap, ymap2);
         if (ev) cudaEventRecord(ev[1], s);
         *launches += 1;
     }
@@ -112,16 +114,38 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             *launches += 1;
         }
         if (ev) cudaEventRecord(ev[2], s);
-        if (p.levels) {
-            kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap);   // energies instead of band signals
+        if (p.weighted) {
+            // fused weighting prefilter: one more warp per CTA (small-band CTA shape only)
+            if constexpr (NBMAX == kTmaSmallBands) {
+                if (p.levels) {
+                    auto kern_lw = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED, true, false>;
+                    e = cudaFuncSetAttribute(kern_lw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+                    if (e != cudaSuccess) return (int)e;
+                    kern_lw<<<grid, threads + 32, smem_a, s>>>(p, tab, xmap, ymap, ymap2);
+                } else {
+                    auto kern_bw = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED, true, false>;
+                    e = cudaFuncSetAttribute(kern_bw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+                    if (e != cudaSuccess) return (int)e;
+                    kern_bw<<<grid, threads + 32, smem_b, s>>>(p, tab, xmap, ymap, ymap2);
+                }
+            }
+        } else if (p.dec_band1) {
+#if PFB_HAS_DEC
+            auto kern_bd = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED, false, true>;
+            e = cudaFuncSetAttribute(kern_bd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+            if (e != cudaSuccess) return (int)e;
+            kern_bd<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap, ymap2);
+#endif
+        } else if (p.levels) {
+            kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap, ymap2);   // energies instead of band signals
         } else if (p.wide) {
             auto kern_w = sos_tma_wide_kernel<PFB_T, PFB_A, K, SCALED>;
-            const int smem_w = (2 + p.nb) * 4 * kTileBytes + 2 * 2 * 8;
+            const int smem_w = (2 + p.nb) * 4 * kTileBytes + 3 * 2 * 8;
             e = cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w);
             if (e != cudaSuccess) return (int)e;
             kern_w<<<grid, threads, smem_w, s>>>(p, tab, xmap, ymap);
         } else {
-            kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap);
+            kern_b<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap, ymap2);
         }
         if (ev) cudaEventRecord(ev[3], s);
         *launches += 1;
@@ -130,17 +154,17 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
 }
 template <int K, int NBMAX>
 static int run_tma_n(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                     cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+                     const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
 #if PFB_HAS_SCALED
-    if (p.gains) return run_tma_ns<K, NBMAX, true>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+    if (p.gains) return run_tma_ns<K, NBMAX, true>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases);
 #endif
-    return run_tma_ns<K, NBMAX, false>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+    return run_tma_ns<K, NBMAX, false>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases);
 }
 template <int K>
 static int run_tma(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                   cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
-    return p.nb <= kTmaSmallBands ? run_tma_n<K, kTmaSmallBands>(p, coef_host, xmap, ymap, s, launches, ev, phases)
-                                  : run_tma_n<K, kTmaMaxBands>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+                   const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    return p.nb <= kTmaSmallBands ? run_tma_n<K, kTmaSmallBands>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases)
+                                  : run_tma_n<K, kTmaMaxBands>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases);
 }
 
 #define PFB_K_SWITCH(CALL)                          \
@@ -170,8 +194,9 @@ int PFB_CAT(launch_scan_, PFB_SUFFIX)(SosParams p, int K, int warps, const doubl
 }
 
 int PFB_CAT(launch_tma_, PFB_SUFFIX)(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap,
-                                     const CUtensorMap &ymap, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
-#define PFB_TMA(k) run_tma<k>(p, coef_host, xmap, ymap, s, launches, ev, phases)
+                                     const CUtensorMap &ymap, const CUtensorMap &ymap2, cudaStream_t s, int *launches,
+                                     cudaEvent_t *ev, int phases) {
+#define PFB_TMA(k) run_tma<k>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases)
     PFB_K_SWITCH(PFB_TMA)
 }
 

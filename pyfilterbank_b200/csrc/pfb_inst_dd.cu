@@ -4,4 +4,5 @@
 #define PFB_SUFFIX dd
 #define PFB_HAS_EXACT true   // the exact (reference rounding) variant only exists when T == A
 #define PFB_HAS_SCALED 1   // gain-normalised TMA kernels need float64 arithmetic
+#define PFB_HAS_DEC 1      // decimating-band output pass (the decimating band path is float64)
 #include "pfb_inst.inl"

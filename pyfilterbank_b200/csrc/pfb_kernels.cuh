@@ -183,6 +183,20 @@ __device__ __forceinline__ void filter_row(char *row, int key, const A (&c)[K][5
     }
 }
 
+// One scipy _linear_filter step (direct form II transposed, a[0] == 1), every product and sum rounded separately
+// in scipy's order: the weighting filters have a 4-fold zero at z = 1, so FMA contraction alone moves the
+// result by ~1e-9 relative.   y = z0 + b0 x ; z[k] = (z[k+1] + x b[k+1]) - y a[k+1] ; z[NZ-1] = x b[NZ] - y a[NZ]
+// (splweighting.weight_signal = scipy.signal.lfilter, pyfilterbank/splweighting.py:80)
+template <int NZ>
+__device__ __forceinline__ double tf_step(double xi, const double (&b)[8], const double (&a)[8], double (&z)[NZ]) {
+    const double yi = __dadd_rn(z[0], __dmul_rn(b[0], xi));
+#pragma unroll
+    for (int k = 0; k < NZ - 1; ++k)
+        z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(xi, b[k + 1])), __dmul_rn(yi, a[k + 1]));
+    z[NZ - 1] = __dsub_rn(__dmul_rn(xi, b[NZ]), __dmul_rn(yi, a[NZ]));
+    return yi;
+}
+
 __device__ __forceinline__ int clamp_i(long long v, int hi) { return v <= 0 ? 0 : (v >= hi ? hi : (int)v); }
 
 // ---------------------------------------------------------------------------------------------

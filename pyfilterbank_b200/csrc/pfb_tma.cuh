@@ -57,7 +57,30 @@ struct TmaParams {
     long long lev_ld, lev_off;
     int ut;
     int wide;             // output pass with 512-byte fragments (sos_tma_wide_kernel); L is then a multiple of 4 half rows
+    // Fused SPL-weighting prefilter (WEIGHT kernels, splweighting.py:61-80): with one chunk per cascade a tile row is
+    // a whole channel, so one extra warp runs the sequential transfer-function recurrence (scipy's operation
+    // order, tf_step) in place on every input tile before the band warps read it -- the weighted signal never
+    // touches HBM.  wz_in [C][8]: delay values at the start of the call (a copy: band group 0 overwrites wz
+    // [C][wnz] with the final ones while other groups may still have to start); taps normalised, wa[0] == 1.
+    int weighted, wnz;
+    const double *wz_in;
+    double *wz;
+    double wb[8], wa[8];
+    // Decimating band (DEC kernels; the anti-alias stage of the decimating band path): band dec_band1 - 1 stores
+    // only its samples of parity dec_phase, through the second output map (time L / 2); 0: none.  Its states live
+    // in dec_states [C][Ktot][2]; the states array then holds Bs = B - 1 bands (Bs == 0 means B).
+    int dec_band1, dec_phase, Bs;
+    void *dec_states;
 };
+
+// States (w1, w2 per section, sections k0..) of cascade (channel, band).
+template <typename A>
+__device__ __forceinline__ A *cascade_states(const TmaParams &p, int chn, int band) {
+    if (p.dec_band1 != 0 && band == p.dec_band1 - 1)
+        return reinterpret_cast<A *>(p.dec_states) + ((size_t)chn * p.Ktot + p.k0) * 2;
+    const int Bs = p.Bs ? p.Bs : p.B;
+    return reinterpret_cast<A *>(p.states) + (((size_t)chn * Bs + band) * p.Ktot + p.k0) * 2;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -193,15 +216,110 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
     }
 }
 
+// Decimating variant of filter_half (MODE 1): every sample is filtered, the samples of parity `phase` of this
+// 128-byte half row (16 doubles / 32 floats -> 64 bytes) are written to 16-byte chunks c0 .. c0 + 3 of the
+// output row (same swizzle).  Tile steps and half rows hold an even number of samples, so the parity of a sample
+// within its vector is its parity within the chunk.
+template <typename T, typename A, int K, bool SCALED>
+__device__ __forceinline__ void filter_half_dec(const char *xrow, char *yrow, int c0, int key, int phase, const A (&c)[K][5],
+                                                A (&w)[K][2]) {
+    using V = typename Vec16<T>::type;
+    constexpr int EPV = Vec16<T>::N;
+    constexpr int kBatch = PFB_ROW_BATCH;
+    static_assert(kBatch % 2 == 0, "two input vectors fill one output vector");
+#pragma unroll
+    for (int v0 = 0; v0 < kVecPerRow; v0 += kBatch) {
+        V in[kBatch];
+#pragma unroll
+        for (int v = 0; v < kBatch; ++v) in[v] = *reinterpret_cast<const V *>(xrow + (((v0 + v) ^ key) << 4));
+#pragma unroll
+        for (int v = 0; v < kBatch; ++v) {
+            T *e = reinterpret_cast<T *>(&in[v]);
+#pragma unroll
+            for (int i = 0; i < EPV; ++i) {
+                A s = (A)e[i];
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    s = SCALED ? scaled_step<A>(s, c[k], w[k][0], w[k][1]) : Biquad<A, false>::step(s, c[k], w[k][0], w[k][1]);
+                if (SCALED) s *= c[0][0];
+                e[i] = (T)s;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < kBatch; v += 2) {
+            V o;
+            T *oe = reinterpret_cast<T *>(&o);
+            const T *e0 = reinterpret_cast<const T *>(&in[v]), *e1 = reinterpret_cast<const T *>(&in[v + 1]);
+#pragma unroll
+            for (int i = 0; i < EPV / 2; ++i) {
+                oe[i] = phase ? e0[2 * i + 1] : e0[2 * i];
+                oe[EPV / 2 + i] = phase ? e1[2 * i + 1] : e1[2 * i];
+            }
+            *reinterpret_cast<V *>(yrow + (((c0 + (v0 + v) / 2) ^ key) << 4)) = o;
+        }
+    }
+}
+
+// Weighting warp: the lane's 128-byte half row of the input tile through the transfer-function recurrence, in
+// place (float32 tiles: float64 arithmetic, the result rounded to float32 like the reference's float path would).
+template <typename T, int NZ>
+__device__ __forceinline__ void weight_half(char *row, int key, const double (&b)[8], const double (&a)[8], double (&z)[NZ]) {
+    using V = typename Vec16<T>::type;
+    constexpr int EPV = Vec16<T>::N;
+    V v[kVecPerRow];
+#pragma unroll
+    for (int i = 0; i < kVecPerRow; ++i) v[i] = *reinterpret_cast<const V *>(row + ((i ^ key) << 4));
+#pragma unroll
+    for (int i = 0; i < kVecPerRow; ++i) {
+        T *e = reinterpret_cast<T *>(&v[i]);
+#pragma unroll
+        for (int j = 0; j < EPV; ++j) e[j] = (T)tf_step<NZ>((double)e[j], b, a, z);
+    }
+#pragma unroll
+    for (int i = 0; i < kVecPerRow; ++i) *reinterpret_cast<V *>(row + ((i ^ key) << 4)) = v[i];
+}
+
+// The weighting warp of a WEIGHT kernel: lane <-> tile row <-> channel (one chunk per cascade).  Waits for the
+// producer's tile (full), filters it in place, hands it to the band warps (wfull).
+template <typename T, int NZ, int NH, int NS>
+__device__ __forceinline__ void weight_warp(const TmaParams &p, char *xs, uint64_t *full, uint64_t *wfull, long long nt,
+                                            int lane, int chn, bool write_back) {
+    constexpr unsigned kStageBytes = NH * kTileBytes;
+    const int key = lane & 7;
+    const bool ok = chn < p.C;
+    double b[8], a[8], z[NZ];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { b[k] = p.wb[k]; a[k] = p.wa[k]; }
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) z[k] = ok ? p.wz_in[(size_t)chn * 8 + k] : 0.0;
+    for (long long t = 0; t < nt; ++t) {
+        const int s = (int)(t % NS);
+        mbar_wait_warp(&full[s], (unsigned)((t / NS) & 1), lane);
+        char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) weight_half<T, NZ>(xrow + h * kTileBytes, key, b, a, z);
+        fence_proxy_async();      // the stage is refilled through the async proxy after the band warps release it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&wfull[s]);
+    }
+    if (ok && write_back) {
+#pragma unroll
+        for (int k = 0; k < NZ; ++k) p.wz[(size_t)chn * NZ + k] = z[k];
+    }
+}
+
 // cta = ((cb * G) + g) * NW + w : channel block cb, band group g, chunk group w.
 // Tile row r <-> chunk JR * w + r % JR of channel CH * cb + r / JR.
 // PASS 0: pre-pass, writes zero-state chunk end states to zs; 1: output pass from zs; 2: like 1 but the band
 // signals are reduced to energies per time unit instead of being stored (band-level epilogue).
 // NH: 128-byte half rows per tile step (2: 256-byte row fragments; 4: 512-byte fragments, which HBM writes ~8 %
 // faster but which need 16 KB output tiles per band warp); NS: input ring stages.
-template <typename T, typename A, int K, int PASS, bool SCALED, int NH = 2, int NS = kTmaStages>
+// WEIGHT: one more warp (index nbw + 1) runs the weighting prefilter on every input tile (weight_warp) and the
+// band warps wait for ITS barrier; DEC: the band p.dec_band1 - 1 stores decimated samples through ymap2.
+template <typename T, typename A, int K, int PASS, bool SCALED, int NH = 2, int NS = kTmaStages, bool WEIGHT = false,
+          bool DEC = false>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
-                                        const CUtensorMap &ymap, char *smem, int cta, int ch0) {
+                                        const CUtensorMap &ymap, const CUtensorMap &ymap2, char *smem, int cta, int ch0) {
     constexpr bool PASS_B = PASS != 0;
     constexpr bool STORE_Y = PASS == 1;
     constexpr int TLEN = kRowBytes / (int)sizeof(T);      // samples per 128-byte half row
@@ -224,12 +342,15 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     char *ys = smem + NS * kStageBytes;               // [nb][2][tile], output pass only
     uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb : 0) * kStageBytes);
     uint64_t *empty = full + NS;
+    uint64_t *wfull = empty + NS;                             // WEIGHT kernels: weighting warp -> band warps
+    uint64_t *in_bar = WEIGHT ? wfull : full;                 // what a band warp waits for
 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], nb_here);
+            if (WEIGHT) mbar_init(&wfull[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -263,6 +384,16 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
         return;
     }
+    if (WEIGHT && warp == nbw + 1) {
+        // ---------------- weighting warp (PASS_B only, JR == 1: lane <-> channel CH * cb + lane) ----------------
+        const int chn = p.CH * cb + lane;
+        switch (p.wnz) {
+            case 4: weight_warp<T, 4, NH, NS>(p, xs, full, wfull, nt, lane, chn, g == 0); break;
+            case 5: weight_warp<T, 5, NH, NS>(p, xs, full, wfull, nt, lane, chn, g == 0); break;
+            default: weight_warp<T, 6, NH, NS>(p, xs, full, wfull, nt, lane, chn, g == 0); break;
+        }
+        return;
+    }
     if (warp >= nb_here) return;
 
     // ---------------- consumers: one band per warp, one (channel, chunk) row per lane ----------------
@@ -270,6 +401,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     const int chn = p.CH * cb + lane / p.JR;
     const bool row_ok = chn < p.C;                // channel blocks may be ragged: TMA clips the tile, lanes idle
     const int q = (row_ok ? chn : 0) * p.B + band;
+    const bool is_dec = DEC && p.dec_band1 != 0 && band == p.dec_band1 - 1;   // warp-uniform
     const int j = p.JR * w + lane % p.JR;
     A c[K][5], wst[K][2];
     // a second, independently reduced copy of the band index that is used for nothing but the
@@ -283,7 +415,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     const double *gain = SCALED ? p.gains + (size_t)band * K * 2 : nullptr;
     if (PASS_B) {
         // a single chunk per cascade starts from the carried-in states themselves (no pre-pass, no carry kernel)
-        const A *z0 = p.J == 1 ? reinterpret_cast<const A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2 : zs;
+        const A *z0 = p.J == 1 ? cascade_states<A>(p, row_ok ? chn : 0, band) : zs;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             wst[k][0] = z0[2 * k];
@@ -312,7 +444,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % NS);
             const unsigned ph = (unsigned)((t / NS) & 1);
-            mbar_wait_warp(&full[s], ph, lane);
+            mbar_wait_warp(&in_bar[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             A acc = A(0);
 #pragma unroll 1   // rolled like the output pass (float32 levels: 13.1 ms unrolled, see profiles/r01h_wait_variants.txt)
@@ -327,11 +459,35 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 tcount = 0;
             }
         }
+    } else if (DEC && is_dec) {
+        // decimating band: a tile step of NH half rows yields NH / 2 half rows of kept samples (one bulk group)
+        static_assert(!DEC || NH % 2 == 0, "decimated half rows pair up");
+        for (long long t = 0; t < nt; ++t) {
+            const int s = (int)(t % NS);
+            const unsigned ph = (unsigned)((t / NS) & 1);
+            mbar_wait_warp(&in_bar[s], ph, lane);
+            const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h)
+                filter_half_dec<T, A, K, SCALED>(xrow + h * kTileBytes, yrow + (h >> 1) * kTileBytes, (h & 1) * 4, key,
+                                                 p.dec_phase, c, wst);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+#pragma unroll
+                for (int o = 0; o < NH / 2; ++o)
+                    tma_store_4d(&ymap2, ybuf + o * kTileBytes, (int)(t * (TT / 2) + o * TLEN), p.JR * w, 0, p.CH * cb);
+                bulk_commit();
+            }
+        }
     } else if (PASS_B) {
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % NS);
             const unsigned ph = (unsigned)((t / NS) & 1);
-            mbar_wait_warp(&full[s], ph, lane);
+            mbar_wait_warp(&in_bar[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             // The tile's NH half rows are stored together at the end of the tile: a row's fragment must reach HBM as
             // one burst (storing each 128-byte half as soon as it is filtered dropped the write efficiency from ~5.0
@@ -382,7 +538,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     if (PASS_B) {
         if (STORE_Y && lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
         if (row_ok && j == p.J - 1) {    // the last chunk ends with the cascade's final state
-            A *st = reinterpret_cast<A *>(p.states) + ((size_t)q * p.Ktot + p.k0) * 2;
+            A *st = cascade_states<A>(p, chn, band);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const A gk = SCALED ? (A)gain[2 * k] : A(1);
@@ -560,12 +716,13 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
 
 // The pre-pass needs no output tiles and few registers: it is compiled for 4 resident CTAs per SM
 // (which also makes ptxas keep the coefficients in uniform registers), the output pass for 2.
-template <typename T, typename A, int K, int PASS, int NBMAX, bool SCALED>
-__global__ void __launch_bounds__((NBMAX + 1) * 32, PASS == 1 ? 2 : PASS == 2 ? 3 : 4)
+template <typename T, typename A, int K, int PASS, int NBMAX, bool SCALED, bool WEIGHT = false, bool DEC = false>
+__global__ void __launch_bounds__((NBMAX + 1 + (WEIGHT ? 1 : 0)) * 32, PASS == 1 ? 2 : PASS == 2 ? 3 : 4)
 sos_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
-               const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+               const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+               const __grid_constant__ CUtensorMap ymap2) {
     extern __shared__ __align__(1024) char smem[];
-    tma_cta<T, A, K, PASS, SCALED>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
+    tma_cta<T, A, K, PASS, SCALED, 2, kTmaStages, WEIGHT, DEC>(p, tab, xmap, ymap, ymap2, smem, blockIdx.x, 0);
 }
 
 // Carry between the two passes: per cascade, s[0] = carried-in state, s[j+1] = P s[j] + z[j];
@@ -585,7 +742,7 @@ __global__ void __launch_bounds__(128) sos_carry_kernel(const TmaParams p) {
     const long long qq = q < p.Q ? q : p.Q - 1;
     const int band = (int)(qq % p.B);
     const A *P = reinterpret_cast<const A *>(p.P) + (size_t)band * S * S;
-    const A *st = reinterpret_cast<const A *>(p.states) + ((size_t)qq * p.Ktot + p.k0) * 2;
+    const A *st = cascade_states<A>(p, (int)(qq / p.B), band);
     A *zs = reinterpret_cast<A *>(p.zs) + (size_t)qq * p.J * S;
     A prow[S];
 #pragma unroll
@@ -629,14 +786,14 @@ __global__ void __launch_bounds__((kTmaMaxBands + 1) * 32, 1)
 sos_tma_wide_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
                     const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
     extern __shared__ __align__(1024) char smem[];
-    tma_cta<T, A, K, 1, SCALED, 4, 2>(p, tab, xmap, ymap, smem, blockIdx.x, 0);
+    tma_cta<T, A, K, 1, SCALED, 4, 2>(p, tab, xmap, ymap, ymap, smem, blockIdx.x, 0);
 }
 
 int launch_tma_dd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+                  const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
 int launch_tma_ff(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+                  const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
 int launch_tma_fd(const TmaParams &p, int K, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                  cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
+                  const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases);
 
 }  // namespace pfb

@@ -174,55 +174,87 @@ class FractionalOctaveFilterbank:
         """(4, 6) anti-alias low-pass applied before every `[::2]`."""
         return butter_sos('lowpass', self.AA_ORDER, self.AA_CUTOFF)
 
+    def _dec_bank(self):
+        """The C-side decimating bank (pfb_decbank_*), built once per design and CUDA device."""
+        dev = torch.cuda.current_device()
+        cache = getattr(self, '_dec_banks', None)
+        if cache is None or cache[0] is not self._dec_plan:
+            cache = (self._dec_plan, {})
+            self._dec_banks = cache
+        if dev not in cache[1]:
+            from ._lib import DecBank
+            K = self.order
+            stage_sos = [None if not st['bands'] else
+                         np.ascontiguousarray(st['sosmat'].T).reshape(len(st['bands']), K, 6) for st in self._dec_plan]
+            cache[1][dev] = DecBank(stage_sos, K, self.aa_sos)
+        return cache[1][dev]
+
     def filter_decimated(self, x, states=None):
         """Per-band decimated analysis of x (N,) or (N, C) (numpy or CUDA tensor).
 
         Returns (bands, states): `bands[b]` is band b at rate fs / decimation_factors[b], shape
         (ceil-length N_b, C); `states` carries the anti-alias states, the decimator phases and the
         band-pass states, so consecutive blocks of any length concatenate to the one-shot result.
-        No band signal is written at the full rate: the anti-alias stage stores every second sample
-        directly (PFB_DECIMATE2) and every stage's bands are filtered from the stage signal."""
+        The whole analysis is ONE call into the library (pfb_decbank_filter): per stage a single pass
+        over the stage signal filters the stage's bands and, as one more band warp with a decimating
+        store, the anti-alias cascade that produces the next stage's signal -- no band signal is ever
+        written at a rate above its own.  `states['aa'][m]` is (C, Kp, 2): the anti-alias cascade is
+        padded with pass-through sections to the bands' section count (their delay values are
+        irrelevant to the output)."""
         plan = self.decimation_plan()
         on_device = isinstance(x, torch.Tensor) and x.is_cuda
         K = self.order
-        if on_device:
-            dev = x.device
-            sig = x.detach().to(torch.float64)
-            sig = sig.reshape(sig.shape[0], -1).t().contiguous()
-        else:
-            dev = _sf._device()
-            a = np.array(x, dtype=np.float64)
-            sig = torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[0], -1).T)).to(dev)
-        C = sig.shape[0]
+        dev = x.device if on_device else _sf._device()
+        sig = _sf.channel_rows(x, dev)
+        C, n = sig.shape
         M = len(plan) - 1
-        aa = self.aa_sos
-        aa_bank = _sf.get_bank(aa.reshape(1, aa.shape[0], 6))
-        if states is None:
-            states = {'aa': [None] * M, 'phase': [0] * M, 'bands': [None] * len(plan)}
-        new = {'aa': [], 'phase': [], 'bands': []}
-        out = [None] * self.num_bands
-        mode = "seq" if self._exact else "auto"
-        for st in plan:
-            m = st['m']
-            if m > 0:
-                ph = int(states['phase'][m - 1])
-                n_in = sig.shape[1]
-                sig3, aa_st = _sf.bank_filter(aa_bank, sig, states['aa'][m - 1], mode=mode, exact=self._exact,
-                                              decimate=ph)
-                sig = sig3[:, 0, :]
-                new['aa'].append(aa_st)
-                new['phase'].append((ph + n_in) % 2)
-            if st['bands']:
+        with torch.cuda.device(dev):
+            dec = self._dec_bank()
+            Kp = dec.Kp
+            if states is None:
+                states = {'aa': [None] * M, 'phase': [0] * M, 'bands': [None] * len(plan)}
+            aa = torch.zeros((max(M, 1), C, Kp, 2), dtype=torch.float64, device=dev)
+            for m in range(M):
+                if states['aa'][m] is not None:
+                    aa[m] = torch.as_tensor(states['aa'][m], dtype=torch.float64, device=dev).reshape(C, Kp, 2)
+            phases = [int(p) for p in states['phase']]
+            new = {'aa': [], 'phase': [], 'bands': []}
+            ys, ldys, y_ptrs, st_ptrs = [], [], [], []
+            nm = n
+            for m, st in enumerate(plan):
                 Bm = len(st['bands'])
-                bank = _sf.get_bank(np.ascontiguousarray(st['sosmat'].T).reshape(Bm, K, 6))
-                y, bst = _sf.bank_filter(bank, sig if sig.is_contiguous() else sig.contiguous(),
-                                         states['bands'][m], mode=mode, exact=self._exact)
-                new['bands'].append(bst)
-                for j, b in enumerate(st['bands']):
-                    yb = y[:, j, :].t()                                   # (N_m, C) view
-                    out[b] = yb if on_device else yb.cpu().numpy()
-            else:
-                new['bands'].append(None)
+                if Bm:
+                    pitch = (nm + 31) // 32 * 32          # 16-byte aligned rows keep the TMA path available
+                    y = torch.empty((C, Bm, max(pitch, 32)), dtype=torch.float64, device=dev)
+                    bst = states['bands'][m]
+                    bst = (torch.zeros((C, Bm, K, 2), dtype=torch.float64, device=dev) if bst is None else
+                           torch.as_tensor(bst, dtype=torch.float64, device=dev).reshape(C, Bm, K, 2).clone())
+                    ys.append((y, nm))
+                    ldys.append(y.stride(1))
+                    y_ptrs.append(y.data_ptr())
+                    st_ptrs.append(bst.data_ptr())
+                    new['bands'].append(bst)
+                else:
+                    ys.append(None)
+                    ldys.append(0)
+                    y_ptrs.append(None)
+                    st_ptrs.append(None)
+                    new['bands'].append(None)
+                if m < M:
+                    nm = max(0, (nm - phases[m] + 1) // 2)
+            flags = _sf._lib.flags_of("seq" if self._exact else "auto", self._exact)
+            dec.filter_ptr(sig.data_ptr(), sig.stride(0) if C > 1 else max(n, 1), y_ptrs, ldys, st_ptrs, aa.data_ptr(),
+                           phases, n, C, flags, torch.cuda.current_stream().cuda_stream)
+        new['aa'] = [aa[m] for m in range(M)]
+        new['phase'] = phases
+        out = [None] * self.num_bands
+        for st, yy in zip(plan, ys):
+            if yy is None:
+                continue
+            y, nm = yy
+            for j, b in enumerate(st['bands']):
+                yb = y[:, j, :nm].t()                                     # (N_m, C) view
+                out[b] = yb if on_device else yb.cpu().numpy()
         return out, new
 
     def set_filterfun(self, filterfun_name):
@@ -252,12 +284,7 @@ class FractionalOctaveFilterbank:
         from . import splweighting as _spl
         b, a = _spl._weighting_coeff_design_funsd[weighting](self.sample_rate)
         on_device = isinstance(x, torch.Tensor) and x.is_cuda
-        if on_device:
-            sig = x.detach().to(torch.float64)
-        else:
-            sig = torch.from_numpy(np.array(x, dtype=np.float64)).to(_sf._device())
-        n = sig.shape[0]
-        rows = sig.reshape(n, -1).t().contiguous()                          # (C, N)
+        rows = _sf.channel_rows(x, x.device if on_device else _sf._device())   # (C, N)
         if weighting_states is not None and not isinstance(weighting_states, torch.Tensor):
             weighting_states = torch.from_numpy(np.array(weighting_states, dtype=np.float64)).to(rows.device)
         wst = None if weighting_states is None else weighting_states.clone()
@@ -269,11 +296,10 @@ class FractionalOctaveFilterbank:
             st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.array(states, dtype=np.float64).flatten('F'))
             st = st.to(device=rows.device, dtype=torch.float64).reshape(C, B, K, 2).clone()
         mode = "seq" if self._exact else "auto"
-        # (Running the weighting in time blocks on a side stream, one block ahead of the bank, was measured: no gain --
-        # the chunked bank loses on short blocks what the overlap wins; the weighting itself is bound by the FP64
-        # issue rate of one warp per 32 channels, ~94 clocks per sample, whatever the channel count.)
-        w, wst = _spl.tf_filter(b, a, rows, wst)
-        yb, st = _sf.bank_filter(bank, w, st, mode=mode, exact=self._exact)
+        # ONE library call (pfb_bank_filter_weighted): with enough channels the prefilter runs as an extra warp of
+        # the bank kernel on the shared-memory input tiles (the weighted signal never touches HBM); with few
+        # channels the weighting kernel and the time-chunked bank run back to back inside the call
+        yb, st, wst = _sf.bank_filter_weighted(bank, rows, b, a, st, wst, mode=mode, exact=self._exact)
         y, st = yb.permute(2, 1, 0), st.reshape(-1)
         if on_device:
             return y, st, wst

@@ -18,19 +18,25 @@ from . import _lib
 from ._lib import Bank
 
 __all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "bank_filter", "bank_levels",
-           "bilinear_sos", "get_bank"]
+           "bank_filter_weighted", "bilinear_sos", "get_bank"]
 
 _bank_cache = collections.OrderedDict()
 
 
-def get_bank(sos):
-    """Bank for sos (B, K, 6) or (C, B, K, 6), cached by content (chunk-transition tables live
-    in the bank, so block-wise callers should not rebuild it every block)."""
+def get_bank(sos, warm_tol=None):
+    """Bank for sos (B, K, 6) or (C, B, K, 6), cached by content, CUDA device and pre-pass tolerance
+    (chunk-transition tables live in the bank, on the device it was created on, so block-wise callers
+    should not rebuild it every block).  warm_tol: relative-L2 budget of the truncated pre-pass of the
+    time-chunked kernels (None: the library default 1e-11; 0: no truncation) -- part of the key, so changing
+    it never alters the accuracy other users of the same coefficients get."""
     sos = np.ascontiguousarray(sos, dtype=np.float64)
-    key = (sos.shape, sos.tobytes())
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    key = (dev, sos.shape, sos.tobytes(), None if warm_tol is None else float(warm_tol))
     bank = _bank_cache.get(key)
     if bank is None:
         bank = Bank(sos)
+        if warm_tol is not None:
+            bank.set_warm_tol(warm_tol)
         _bank_cache[key] = bank
         if len(_bank_cache) > 32:
             _bank_cache.popitem(last=False)
@@ -43,6 +49,53 @@ def _device():
     if not torch.cuda.is_available():
         raise _lib.PfbError("no CUDA device: pyfilterbank_b200 has no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def _signal_types(x, arith64):
+    if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("x must be a (C, N) CUDA tensor with contiguous rows")
+    if x.dtype == torch.float64:
+        return _lib.PFB_F64, torch.float64
+    if x.dtype == torch.float32:
+        return _lib.PFB_F32, (torch.float64 if arith64 else torch.float32)
+    raise ValueError("x must be float32 or float64")
+
+
+def _check_states(states, sdt, C, B, K, device):
+    if states is None:
+        return torch.zeros((C, B, K, 2), dtype=sdt, device=device)
+    if (not isinstance(states, torch.Tensor) or not states.is_cuda or states.dtype != sdt or not states.is_contiguous()
+            or states.numel() != C * B * K * 2):
+        raise ValueError("states must be a contiguous CUDA %s tensor with C*B*K*2 elements" % sdt)
+    return states
+
+
+def bank_filter_weighted(bank, x, b, a, states=None, wz=None, *, mode="auto", exact=False, arith64=False, out=None):
+    """y = bank(lfilter(b, a, x)): the SPL-weighting prefilter (splweighting.py:61-80) and the bank as ONE call
+    (pfb_bank_filter_weighted).  x (C, N) CUDA tensor, float64 or float32 (the prefilter always runs in float64
+    arithmetic); wz (C, ntaps - 1) float64 delay values in scipy's zi convention, in/out (None: zeros).
+    Returns (y (C, B, N), states, wz)."""
+    dtype, sdt = _signal_types(x, arith64)
+    C, N = x.shape
+    B, K = bank.B, bank.K
+    states = _check_states(states, sdt, C, B, K, x.device)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    nz = max(max(len(b), len(a)) - 1, 1)
+    if wz is None:
+        wz = torch.zeros((C, nz), dtype=torch.float64, device=x.device)
+    elif wz.dtype != torch.float64 or not wz.is_contiguous() or wz.numel() != C * nz or not wz.is_cuda:
+        raise ValueError("wz must be a contiguous CUDA float64 tensor with C*(ntaps-1) elements")
+    if out is None:
+        pitch = (N + 31) // 32 * 32              # 16-byte aligned rows keep the TMA path available
+        out = torch.empty((C, B, pitch), dtype=x.dtype, device=x.device)[:, :, :N]
+    ldx = x.stride(0) if C > 1 else max(N, 1)
+    if N > 0:
+        with torch.cuda.device(x.device):
+            bank.filter_weighted_ptr(dtype, x.data_ptr(), ldx, out.data_ptr(), max(out.stride(1), N, 1), states.data_ptr(),
+                                     b, a, wz.data_ptr(), N, C, _lib.flags_of(mode, exact, arith64),
+                                     torch.cuda.current_stream().cuda_stream)
+    return out, states, wz
 
 
 def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False, out=None, decimate=None):
@@ -67,7 +120,8 @@ def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False
         raise ValueError("states must be a contiguous %s tensor with C*B*K*2 elements" % sdt)
     n_out = N if decimate is None else max(0, (N - int(decimate) + 1) // 2)
     if out is None:
-        out = torch.empty((C, B, n_out), dtype=x.dtype, device=x.device)
+        pitch = (n_out + 31) // 32 * 32          # 16-byte aligned rows keep the TMA kernels available for any N
+        out = torch.empty((C, B, pitch), dtype=x.dtype, device=x.device)[:, :, :n_out]
     ldx = x.stride(0) if C > 1 else max(N, 1)
     # a decimated block can be empty (one input sample on the odd phase): states still advance
     dst = out if out.numel() else torch.empty(1, dtype=x.dtype, device=x.device)
@@ -93,8 +147,7 @@ def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
         raise ValueError("x must be float32 or float64")
     block_len = N if block_len is None else int(block_len)
     B, K = bank.B, bank.K
-    if states is None:
-        states = torch.zeros((C, B, K, 2), dtype=sdt, device=x.device)
+    states = _check_states(states, sdt, C, B, K, x.device)
     nblocks = N // block_len if block_len > 0 else 0
     out = torch.empty((C, B, max(nblocks, 1)), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
@@ -102,6 +155,25 @@ def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
                         states.data_ptr(), N, C, block_len, _lib.flags_of("auto", False, arith64),
                         torch.cuda.current_stream().cuda_stream)
     return out[:, :, :nblocks], states
+
+
+def channel_rows(sig, dev, dtype=torch.float64):
+    """(N, C) or (N,) signal (numpy array or tensor, host or device) -> (C, N) CUDA tensor view of a buffer whose
+    row pitch is a multiple of 32 elements: every row starts 16-byte aligned whatever N is, which keeps the
+    TMA kernels available (unaligned rows fall back to the cp.async kernels)."""
+    if not isinstance(sig, torch.Tensor):
+        sig = torch.from_numpy(np.asarray(sig))
+    sig = sig.detach()
+    n = sig.shape[0]
+    src = sig.reshape(n, -1)
+    C = src.shape[1]
+    pitch = max(32, (n + 31) // 32 * 32)
+    rows = torch.empty((C, pitch), dtype=dtype, device=dev)[:, :n]
+    if src.is_cuda:
+        rows.copy_(src.t())
+    else:
+        rows.copy_(src.t().contiguous().to(dtype))      # one contiguous host-to-device copy
+    return rows
 
 
 def _to_host(t):
@@ -187,11 +259,7 @@ def sosfilter_double_mimo_c(signal, sos, states=None, *, mode="auto", exact=Fals
             raise ValueError("sos has %d channels, signal has %d" % (sos.shape[2], nchan))
         bank_sos = np.ascontiguousarray(sos.transpose(2, 1, 0)).reshape(nchan, kbands, ksos, 6)
     bank = get_bank(bank_sos)
-    if on_device:
-        x = signal.detach().to(torch.float64).reshape(nframes, nchan).t().contiguous()
-    else:
-        x = torch.from_numpy(np.ascontiguousarray(
-            np.array(signal, dtype=np.float64).reshape(nframes, nchan).T)).to(dev)
+    x = channel_rows(signal, dev)
     nst = nchan * kbands * ksos * 2
     if states is None:
         st = torch.zeros(nst, dtype=torch.float64, device=dev)

@@ -71,8 +71,8 @@ def cfg3_dec(C=1024, seconds=4):
     load = float((1.0 / ofb.decimation_factors).sum())
     ms = timeit(lambda: ofb.filter_decimated(x), iters=2, warm=1)
     alg = C * n * 8 * (1 + load)
-    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s f64" % (C, seconds), ms, C * ofb.num_bands * n, alg,
-           {"band_equivalents": load, "bands": ofb.num_bands})
+    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s f64%s" % (C, seconds, " (unfused)" if os.environ.get("PFB_DEC_UNFUSED") else ""),
+           ms, C * ofb.num_bands * n, alg, {"band_equivalents": load, "bands": ofb.num_bands, "dec": ofb._dec_bank().info()})
 
 
 def cfg3_stream(C=1024, block_s=3, blocks=10):
@@ -107,29 +107,50 @@ def cfg4(C=512, seconds=10):
            C * n * (8 + 16 * B))
 
 
-def cfg5(C=1024, seconds=5, dtype=torch.float64):
+def cfg5(C=1024, seconds=5, dtype=torch.float64, fused=None):
+    """A-weighting + 1/3-octave bank through pfb_bank_filter_weighted (one call).  fused: None = planner's choice,
+    True / False force the fused kernel / the weighting kernel + chunked bank."""
     ofb = p.FractionalOctaveFilterbank(sample_rate=48000)
     B, K, n = 33, 4, 48000 * seconds
-    bank = p.Bank(np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6))
+    bank = p.get_bank(np.ascontiguousarray(ofb.sosmat.T).reshape(B, K, 6))
     b, a = spl.a_weighting_coeffs_design(48000)
-    x = torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1
+    x = (torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1).to(dtype)
     y = torch.empty(C, B, n, device="cuda", dtype=dtype)
     esz = 8 if dtype == torch.float64 else 4
+    if fused is None:
+        os.environ.pop("PFB_WEIGHT_FUSED", None)
+    else:
+        os.environ["PFB_WEIGHT_FUSED"] = "1" if fused else "0"
+    ms = timeit(lambda: p.bank_filter_weighted(bank, x, b, a, out=y), iters=3, warm=1)
+    info = bank.last_launch()
+    os.environ.pop("PFB_WEIGHT_FUSED", None)
+    msw = timeit(lambda: spl.tf_filter(b, a, x.to(torch.float64)), iters=2, warm=1) if C <= 1024 else None
+    report("cfg5 A-weighting + 1/3-oct bank, %d ch x %d s, %s, fused=%s nb=%s" % (
+               C, seconds, "f64" if esz == 8 else "f32", fused, os.environ.get("PFB_TMA_NB", "auto")), ms,
+           C * B * n, C * n * esz * (B + 1), {"weighting_kernel_alone_ms": msw, "launch": info})
 
-    def run():
-        if dtype == torch.float64:      # the product call: weighting one time block ahead of the bank on a side stream
-            ofb.filter_mimo_c(x.t(), weighting='A')
-        else:
-            w, _ = spl.tf_filter(b, a, x)
-            p.bank_filter(bank, w.to(dtype), None, out=y)
-    ms = timeit(run, iters=2, warm=1)
-    msw = timeit(lambda: spl.tf_filter(b, a, x), iters=2, warm=1)
-    report("cfg5 A-weighting + 1/3-oct bank, %d ch x %d s, %s" % (C, seconds, "f64" if esz == 8 else "f32 bank"), ms,
-           C * B * n, C * n * (8 + esz * B), {"weighting_kernel_ms": msw, "launch": bank.last_launch()})
+
+def cfg5_sweep():
+    for dtype in (torch.float64, torch.float32):
+        for C in (1024, 2048, 4096):
+            cfg5(C=C, seconds=5 if C <= 2048 else 2, dtype=dtype)
+            torch.cuda.empty_cache()
+        cfg5(dtype=dtype, fused=False)
+        for nb in (3, 4, 5, 6):
+            os.environ["PFB_TMA_NB"] = str(nb)
+            cfg5(dtype=dtype, fused=True)
+            torch.cuda.empty_cache()
+        os.environ.pop("PFB_TMA_NB", None)
+
+
+def cfg3_unfused(C=1024, seconds=3):
+    os.environ["PFB_DEC_UNFUSED"] = "1"
+    cfg3_dec(C, seconds)
+    os.environ.pop("PFB_DEC_UNFUSED", None)
 
 
 CASES = {"cfg1": cfg1, "cfg3_full": cfg3_full, "cfg3_dec": cfg3_dec, "cfg3_stream": cfg3_stream, "cfg4": cfg4, "cfg5": cfg5,
-         "cfg5_f32": lambda: cfg5(dtype=torch.float32)}
+         "cfg5_f32": lambda: cfg5(dtype=torch.float32), "cfg5_sweep": cfg5_sweep, "cfg3_unfused": cfg3_unfused}
 if __name__ == "__main__":
     for name in (sys.argv[1:] or list(CASES)):
         CASES[name]()

@@ -91,5 +91,42 @@ while time.time() < t_end:
     if not np.max(np.abs(e - e0) / scale) <= 2e-9:
         print("FAIL levels C=%d bl=%d nblk=%d err=%.2e" % (C, bl, nblk, np.max(np.abs(e - e0) / scale))); sys.exit(1)
     lev_cases += 1
-print("gammatone cases %d, band-level cases %d" % (fos_cases, lev_cases))
+# fused callers: weighting prefilter + bank (fused kernel forced or planner's choice), decimating band path
+from pyfilterbank_b200 import splweighting as spl
+t_end = time.time() + float(os.environ.get("SECONDS_FUSED", 30))
+fused_cases = dec_cases = 0
+ofb48 = p.FractionalOctaveFilterbank(sample_rate=48000)
+while time.time() < t_end:
+    C = int(rng.choice([1, 2, 31, 32, 33, 70, 129])); n = int(rng.choice([130, 1000, 4096, 5001, 20000, 65536]))
+    wname = str(rng.choice(["A", "B", "C"]))
+    b, a = spl._weighting_coeff_design_funsd[wname](48000)
+    os.environ["PFB_WEIGHT_FUSED"] = str(int(rng.integers(0, 2)))
+    x = rng.standard_normal((n, C))
+    chans = sorted({0, C - 1})
+    _, y0, _ = oracle.weighted_bank(x[:, chans], b, a, ofb48.sosmat)
+    cut = int(rng.integers(1, n))
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).cuda()
+    ya, st, wz = p.bank_filter_weighted(bank48, xt[:, :cut].contiguous(), b, a)
+    yb, st, wz = p.bank_filter_weighted(bank48, xt[:, cut:].contiguous(), b, a, st, wz)
+    yy = torch.cat([ya, yb], dim=2)[chans].cpu().numpy()
+    e = max(rel(yy[:, k].T, y0[:, k]) for k in range(33))
+    if not e <= 1e-9:
+        print("FAIL weighted %s C=%d n=%d cut=%d fused=%s err=%.2e" % (wname, C, n, cut, os.environ["PFB_WEIGHT_FUSED"], e)); sys.exit(1)
+    fused_cases += 1
+    if rng.random() < 0.5:
+        C = int(rng.choice([1, 3, 32, 40])); n = int(rng.choice([1, 17, 1000, 4096, 20001, 100000]))
+        x = rng.standard_normal((n, C))
+        chans = sorted({0, C - 1})
+        ref = oracle.decimated_bank(x[:, chans], ofb48.decimation_plan(), ofb48.aa_sos, 4)
+        cut = int(rng.integers(0, n + 1))
+        ba, sd = ofb48.filter_decimated(torch.from_numpy(x[:cut]).cuda()) if cut else ([None] * 33, None)
+        bb, sd = ofb48.filter_decimated(torch.from_numpy(x[cut:]).cuda(), sd) if cut < n else ([None] * 33, sd)
+        for k in range(33):
+            parts = [t[:, chans].cpu().numpy() for t in (ba[k], bb[k]) if t is not None]
+            yk = np.concatenate(parts)
+            if yk.shape != ref[k].shape or not rel(yk, ref[k]) <= 1e-9:
+                print("FAIL decimated C=%d n=%d cut=%d band=%d err=%.2e" % (C, n, cut, k, rel(yk, ref[k]) if yk.shape == ref[k].shape else -1)); sys.exit(1)
+        dec_cases += 1
+os.environ.pop("PFB_WEIGHT_FUSED", None)
+print("gammatone cases %d, band-level cases %d, weighted cases %d, decimated cases %d" % (fos_cases, lev_cases, fused_cases, dec_cases))
 print("fuzz ok: %d cases, worst band error %.2e, launch kinds (mode, path) %s" % (cases, worst, modes))
