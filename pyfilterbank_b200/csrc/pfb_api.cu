@@ -177,7 +177,14 @@ double *pfb_bank::gains_only(int arith) {
         return nullptr;
     }
     if (counted_malloc((void **)&gains_dev[0], g.size() * sizeof(double)) != cudaSuccess) return nullptr;
-    cudaMemcpy(gains_dev[0], g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice);
+    // (pageable-memory copies may return before the DMA has landed; the kernels run on streams that do not
+    // synchronise with the NULL stream, hence the explicit wait -- once per bank)
+    if (cudaMemcpy(gains_dev[0], g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaStreamSynchronize(0) != cudaSuccess) {
+        cudaFree(gains_dev[0]);
+        gains_dev[0] = nullptr;
+        return nullptr;
+    }
     return gains_dev[0];
 }
 
@@ -288,6 +295,7 @@ int ensure_coef(pfb_bank *b, int arith) {
         PFB_CUDA(counted_malloc(&d, n * sizeof(float)));
         PFB_CUDA(cudaMemcpy(d, f.data(), n * sizeof(float), cudaMemcpyHostToDevice));
     }
+    PFB_CUDA(cudaStreamSynchronize(0));   // the upload has landed before any stream's kernel reads it
     b->coef[arith] = d;
     return PFB_OK;
 }
@@ -326,12 +334,21 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
     for (auto &kv : b->tables) cached_bytes += kv.second.bytes;
     // bound the cache (block-wise callers with a fixed block length hit it; the segment loop of the band-level path
     // and the host-streaming paths add a handful of chunk lengths each); nothing may still be using the old tables
-    if (b->tables.size() >= 96 || cached_bytes > (1ULL << 30)) {
+    if (b->tables.size() >= 96 || cached_bytes > (3ULL << 30)) {
         PFB_CUDA(cudaDeviceSynchronize());
         for (auto &kv : b->tables) free_tables(kv.second);
         b->tables.clear();
     }
     Tables t;
+    // on a CUDA error the partial allocations held in t are released before returning
+#define PFB_CUDA_T(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            free_tables(t);                                                                      \
+            return fail(PFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                        \
+    } while (0)
     // float32 arithmetic: 1e-6, two orders under its 1e-4 parity budget (float64: 1e-11 under 1e-9)
     const double tol = arith == PFB_F64 ? b->warm_tol : (b->warm_tol > 0 ? std::max(b->warm_tol, 1e-6) : 0.0);
     // rows with identical coefficients (a bank tiled per channel) share their tables
@@ -361,17 +378,17 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
             t.warm_total += std::min<long long>(warm[r], L);
         }
         int *dw = nullptr;
-        PFB_CUDA(counted_malloc(&dw, b->rows * sizeof(int)));
-        PFB_CUDA(cudaMemcpy(dw, warm.data(), b->rows * sizeof(int), cudaMemcpyHostToDevice));
+        PFB_CUDA_T(counted_malloc(&dw, b->rows * sizeof(int)));
+        PFB_CUDA_T(cudaMemcpy(dw, warm.data(), b->rows * sizeof(int), cudaMemcpyHostToDevice));
         t.warm.push_back(dw);
         void *d = nullptr;
         if (arith == PFB_F64) {
-            PFB_CUDA(counted_malloc(&d, n * sizeof(double)));
-            PFB_CUDA(cudaMemcpy(d, Pd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+            PFB_CUDA_T(counted_malloc(&d, n * sizeof(double)));
+            PFB_CUDA_T(cudaMemcpy(d, Pd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
         } else {
             std::vector<float> Pf(Pd.begin(), Pd.end());
-            PFB_CUDA(counted_malloc(&d, n * sizeof(float)));
-            PFB_CUDA(cudaMemcpy(d, Pf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+            PFB_CUDA_T(counted_malloc(&d, n * sizeof(float)));
+            PFB_CUDA_T(cudaMemcpy(d, Pf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         }
         t.P.push_back(d);
     }
@@ -383,7 +400,7 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
         const long long nt = L / tt;
         std::vector<long long> off(b->rows);
         std::vector<int> hwarm(b->rows);
-        PFB_CUDA(cudaMemcpy(hwarm.data(), t.warm[0], b->rows * sizeof(int), cudaMemcpyDeviceToHost));
+        PFB_CUDA_T(cudaMemcpy(hwarm.data(), t.warm[0], b->rows * sizeof(int), cudaMemcpyDeviceToHost));
         long long total = 0;
         for (int r = 0; r < b->rows; ++r) {
             off[r] = total;
@@ -391,7 +408,8 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
             if (wt > nt) wt = nt;
             total += wt * tt * MT * 8;
         }
-        if (total > 0 && total * 8 <= (256LL << 20)) {
+        // (cap: a 119-band order-6 bank on few channels x 30 s needs ~340 MB; beyond the cap the recurrence pre-pass runs)
+        if (total > 0 && total * 8 <= ((long long)env_int("PFB_HFORM_MAX_MB", 1024) << 20)) {
             std::vector<double> Hh((size_t)total, 0.0), Hm;
             for (int r = 0; r < b->rows; ++r) {
                 long long wt = ((long long)hwarm[r] + tt - 1) / tt;
@@ -408,12 +426,14 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
                 }
             }
             t.bytes += (size_t)total * sizeof(double);
-            PFB_CUDA(counted_malloc((void **)&t.H, (size_t)total * sizeof(double)));
-            PFB_CUDA(cudaMemcpy(t.H, Hh.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
-            PFB_CUDA(counted_malloc((void **)&t.Hoff, b->rows * sizeof(long long)));
-            PFB_CUDA(cudaMemcpy(t.Hoff, off.data(), b->rows * sizeof(long long), cudaMemcpyHostToDevice));
+            PFB_CUDA_T(counted_malloc((void **)&t.H, (size_t)total * sizeof(double)));
+            PFB_CUDA_T(cudaMemcpy(t.H, Hh.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice));
+            PFB_CUDA_T(counted_malloc((void **)&t.Hoff, b->rows * sizeof(long long)));
+            PFB_CUDA_T(cudaMemcpy(t.Hoff, off.data(), b->rows * sizeof(long long), cudaMemcpyHostToDevice));
         }
     }
+    PFB_CUDA_T(cudaStreamSynchronize(0));   // pageable uploads have landed before any stream's kernel reads the tables
+#undef PFB_CUDA_T
     auto ins = b->tables.emplace(key, std::move(t));
     *out = &ins.first->second;
     return PFB_OK;

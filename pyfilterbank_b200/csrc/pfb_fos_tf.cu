@@ -226,6 +226,7 @@ int launch_fos(const FosParams &p, int order, bool aligned, cudaStream_t s) {
         case 4: return (int)run_fos<4>(p, aligned, s);
         case 5: return (int)run_fos<5>(p, aligned, s);
         case 6: return (int)run_fos<6>(p, aligned, s);
+        case 7: return (int)run_fos<7>(p, aligned, s);
         case 8: return (int)run_fos<8>(p, aligned, s);
         default: return (int)cudaErrorInvalidValue;
     }
@@ -460,6 +461,9 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
             e = cudaMalloc(&tb.dev, tb.offW + w_bytes);
             if (e == cudaSuccess) e = cudaMemcpy(tb.dev, P.data(), P_bytes, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy((char *)tb.dev + tb.offW, warm.data(), w_bytes, cudaMemcpyHostToDevice);
+            // copies from pageable memory may return before the DMA has landed, and the kernels below run on streams
+            // that do not synchronise with the NULL stream
+            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
             if (e != cudaSuccess) {
                 if (tb.dev) cudaFree(tb.dev);
                 plan.by_len.erase(Lt);
@@ -485,6 +489,7 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
         case 4: err = run_fos_tma<4>(p, tab, cp, xmap, ymap, s, wide); break;
         case 5: err = run_fos_tma<5>(p, tab, cp, xmap, ymap, s, wide); break;
         case 6: err = run_fos_tma<6>(p, tab, cp, xmap, ymap, s, wide); break;
+        case 7: err = run_fos_tma<7>(p, tab, cp, xmap, ymap, s, wide); break;
         case 8: err = run_fos_tma<8>(p, tab, cp, xmap, ymap, s, wide); break;
         default: err = (int)cudaErrorInvalidValue;
     }
@@ -551,8 +556,8 @@ int pfb_fos_bank_c128(const double *x, int64_t ldx, double *y, int64_t ldy, cons
     if (n == 0) return pfb_set_error(PFB_OK, "");
     if (!x || !y || !coef_host || !states || B <= 0 || C <= 0 || n < 0 || ldx < n || ldy < n)
         return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: bad argument");
-    if (order < 1 || order == 7 || order > 8)
-        return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: order must be 1..6 or 8");
+    if (order < 1 || order > 8)
+        return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: order must be 1..8 per call (longer cascades are chained by the caller)");
     if ((long long)C * B > 0x7fffffffLL) return pfb_set_error(PFB_ERR_INVALID, "pfb_fos_bank_c128: C*B too large");
     cudaStream_t s = (cudaStream_t)stream;
     // TMA path: 16-byte aligned input rows (output rows are complex = 16 bytes per element)

@@ -74,16 +74,13 @@ def design_filtbank_coeffs(samplerate, order, centerfrequencies, bandwidths=None
                             attenuation_half_bandwidth_db=attenuation_half_bandwidth_db)
 
 
-def fos_bank(x, coef, order, states=None):
-    """Run B complex one-pole cascades over every row of x.
+_MAX_ORDER_PER_CALL = 8     # cascade length of one pfb_fos_bank_c128 launch; longer cascades are chained
 
-    x (C, N) CUDA float64 tensor; coef (B, 3) numpy rows (gain, Re c, Im c); states (C, B, order)
-    complex128 CUDA tensor or None.  Returns (bands (C, B, N) complex128, states)."""
+
+def _fos_bank_real(x, coef, order, states):
+    """One library call: B complex one-pole cascades of `order` <= 8 stages over every row of the REAL (C, N) x."""
     C, N = x.shape
-    coef = np.ascontiguousarray(coef, dtype=np.float64)
     B = coef.shape[0]
-    if states is None:
-        states = torch.zeros((C, B, order), dtype=torch.complex128, device=x.device)
     y = torch.empty((C, B, N), dtype=torch.complex128, device=x.device)
     if N > 0:
         x = x.contiguous()
@@ -91,6 +88,48 @@ def fos_bank(x, coef, order, states=None):
             _lib.check(_lib.lib().pfb_fos_bank_c128(x.data_ptr(), N, y.data_ptr(), N, coef.ctypes.data, B, order,
                                                      states.data_ptr(), N, C,
                                                      torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+def fos_bank(x, coef, order, states=None):
+    """Run B complex one-pole cascades over every row of x.
+
+    x (C, N) CUDA tensor, float64 or complex128; coef (B, 3) numpy rows (gain, Re c, Im c); states (C, B, order)
+    complex128 CUDA tensor or None (updated in place).  Returns (bands (C, B, N) complex128, states).
+
+    The kernels take real rows and cascades of up to 8 stages.  The cascade is linear over the complex numbers,
+    so a complex input is filtered as F(Re x) + i F(Im x) (the carried-in states go with the real part), which is
+    what `reanalyze` needs (gammatone.py:318-321 feeds complex bands to lfilter); cascades of more than 8 stages
+    run as 8 stages followed by the remaining stages with gain 1 on that complex intermediate, one band at a
+    time.  Both compositions differ from the reference's single complex recurrence only in the rounding of the
+    sums of separately rounded parts (~1e-16 relative)."""
+    C, N = x.shape
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    B = coef.shape[0]
+    if states is None:
+        states = torch.zeros((C, B, order), dtype=torch.complex128, device=x.device)
+    if order <= _MAX_ORDER_PER_CALL:
+        if not x.is_complex():
+            return _fos_bank_real(x.to(torch.float64), coef, order, states), states
+        zero = torch.zeros_like(states)
+        y = _fos_bank_real(x.real.to(torch.float64), coef, order, states)
+        y = y + 1j * _fos_bank_real(x.imag.to(torch.float64), coef, order, zero)
+        states += 1j * zero
+        return y, states
+    # long cascade: stages [0, 8) on the input, then the rest with gain 1, band by band (each band has its own input)
+    head = states[:, :, :_MAX_ORDER_PER_CALL].contiguous()
+    y, head = fos_bank(x, coef, _MAX_ORDER_PER_CALL, head)
+    states[:, :, :_MAX_ORDER_PER_CALL] = head
+    k0 = _MAX_ORDER_PER_CALL
+    while k0 < order:
+        k = min(_MAX_ORDER_PER_CALL, order - k0)
+        for b in range(B):
+            st = states[:, b:b + 1, k0:k0 + k].contiguous()
+            unit = np.array([[1.0, coef[b, 1], coef[b, 2]]])
+            yb, st = fos_bank(y[:, b], unit, k, st)
+            y[:, b] = yb[:, 0]
+            states[:, b:b + 1, k0:k0 + k] = st
+        k0 += k
     return y, states
 
 
@@ -104,12 +143,7 @@ def fosfilter(b, a, order, signal, states=None):
     CUDA tensors out."""
     on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
     dev = signal.device if on_device else _device()
-    if on_device:
-        if signal.is_complex():
-            signal = signal.real
-        x = signal.to(torch.float64).reshape(1, -1)
-    else:
-        x = torch.from_numpy(np.ascontiguousarray(np.real(signal), dtype=np.float64).reshape(1, -1)).to(dev)
+    x = _as_rows(signal, dev).reshape(1, -1)
     st = None
     if states is not None:
         st = torch.as_tensor(np.asarray(states.cpu() if isinstance(states, torch.Tensor) else states,
@@ -117,6 +151,21 @@ def fosfilter(b, a, order, signal, states=None):
     y, st = fos_bank(x, _coef_rows([(b, a)]), order, st)
     y, st = y.reshape(-1), st.reshape(order)
     return (y, st) if on_device else (y.cpu().numpy(), st.cpu().numpy())
+
+
+def _as_rows(signal, dev):
+    """numpy array or tensor -> CUDA float64 tensor, or complex128 when the input has a non-zero imaginary part
+    (the reference's lfilter filters complex signals; a complex input with zero imaginary part takes the real path,
+    like the impulse the constructor analyses)."""
+    if isinstance(signal, torch.Tensor):
+        t = signal.detach().to(dev)
+        if t.is_complex():
+            return t.to(torch.complex128) if bool((t.imag != 0).any()) else t.real.to(torch.float64)
+        return t.to(torch.float64)
+    a = np.asarray(signal)
+    if np.iscomplexobj(a) and np.any(a.imag != 0):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).to(dev)
+    return torch.from_numpy(np.ascontiguousarray(np.real(a), dtype=np.float64)).to(dev)
 
 
 def _create_impulse(num_samples):
@@ -155,10 +204,7 @@ class GammatoneFilterbank:
     def analyze(self, signal, states=None):
         on_device = isinstance(signal, torch.Tensor) and signal.is_cuda
         dev = signal.device if on_device else _device()
-        if on_device:
-            x = (signal.real if signal.is_complex() else signal).to(torch.float64)
-        else:
-            x = torch.from_numpy(np.ascontiguousarray(np.real(signal), dtype=np.float64)).to(dev)
+        x = _as_rows(signal, dev)
         batched = x.dim() == 2
         x = x.reshape(-1, x.shape[-1])
         C, B = x.shape[0], len(self._coeffs)
@@ -173,6 +219,25 @@ class GammatoneFilterbank:
         for i in range(B):
             band = y[:, i] if batched else y[0, i]
             yield band, (st[:, i] if batched else st[0, i])
+
+    def reanalyze(self, bands, states=None):
+        """Every band through ITS OWN cascade once more (gammatone.py:318-321): `bands` is the sequence of complex
+        (N,) bands `analyze` yields (or (C, N) batches), `states` the matching sequence of state arrays.  Generator
+        of (band, states) like `analyze`."""
+        for i, ((b, a), band) in enumerate(zip(self._coeffs, bands)):
+            on_device = isinstance(band, torch.Tensor) and band.is_cuda
+            dev = band.device if on_device else _device()
+            x = _as_rows(band, dev)
+            batched = x.dim() == 2
+            x = x.reshape(-1, x.shape[-1])
+            st = None
+            if states is not None and len(states):
+                s_i = states[i]
+                s_i = np.asarray(s_i.cpu() if isinstance(s_i, torch.Tensor) else s_i, dtype=np.complex128)
+                st = torch.as_tensor(s_i.reshape(x.shape[0], 1, self.order)).to(dev)
+            y, st = fos_bank(x, self._coef_rows[i:i + 1], self.order, st)
+            y, st = (y[:, 0], st[:, 0]) if batched else (y[0, 0], st[0, 0])
+            yield (y, st) if on_device else (y.cpu().numpy(), st.cpu().numpy())
 
     # ------------------------------------------------------------------------------------------
     # synthesis side (gammatone.py:323-340)

@@ -126,7 +126,8 @@ def cfg5(C=1024, seconds=5, dtype=torch.float64, fused=None):
     os.environ.pop("PFB_WEIGHT_FUSED", None)
     msw = timeit(lambda: spl.tf_filter(b, a, x.to(torch.float64)), iters=2, warm=1) if C <= 1024 else None
     report("cfg5 A-weighting + 1/3-oct bank, %d ch x %d s, %s, fused=%s nb=%s" % (
-               C, seconds, "f64" if esz == 8 else "f32", fused, os.environ.get("PFB_TMA_NB", "auto")), ms,
+               C, seconds, "f64" if esz == 8 else "f32", fused, os.environ.get("PFB_TMA_NB", "auto")) +
+           (" J=1" if os.environ.get("PFB_TMA_J") else ""), ms,
            C * B * n, C * n * esz * (B + 1), {"weighting_kernel_alone_ms": msw, "launch": info})
 
 
@@ -136,6 +137,9 @@ def cfg5_sweep():
             cfg5(C=C, seconds=5 if C <= 2048 else 2, dtype=dtype)
             torch.cuda.empty_cache()
         cfg5(dtype=dtype, fused=False)
+        os.environ["PFB_TMA_J"] = "1"          # the unfused bank forced to one chunk per cascade (the fused kernel's tile shape)
+        cfg5(dtype=dtype, fused=False)
+        os.environ.pop("PFB_TMA_J", None)
         for nb in (3, 4, 5, 6):
             os.environ["PFB_TMA_NB"] = str(nb)
             cfg5(dtype=dtype, fused=True)

@@ -399,3 +399,69 @@ def test_bank_runs_are_bitwise_reproducible(pfb, dtype):
     y = ofb.filter_mimo_c(x)[0]
     for _ in range(3):
         assert torch.equal(y, ofb.filter_mimo_c(x)[0])
+
+
+def _fosfilter_scipy(b, a, order, signal, states=None):
+    """The reference's fosfilter (gammatone.py:196-237) with the `if not states` bug side-stepped: scipy's lfilter
+    `order` times, gain in the first pass only; real or complex input."""
+    from scipy.signal import lfilter
+    st = np.zeros(order, np.complex128) if states is None else np.array(states, np.complex128)
+    sig, bb = signal, b
+    for i in range(order):
+        sig, z = lfilter(bb, a, sig, zi=[st[i]])
+        st[i] = z[0]
+        bb = np.ones_like(b)
+    return sig, st
+
+
+@pytest.mark.parametrize("order", [7, 10, 13])
+def test_gammatone_any_order(pfb, order):
+    """The reference takes any order (gammatone.py:232); orders above 8 chain two launches per band."""
+    from pyfilterbank_b200 import gammatone as gt
+    rng = np.random.default_rng(order)
+    coeffs = list(gt.design_filtbank_coeffs(16000, order, [200.0, 1000.0, 3000.0], bandwidth_factor=1.0))
+    rows = gt._coef_rows(coeffs)
+    x = rng.standard_normal((3, 6000))
+    y, st = gt.fos_bank(torch.from_numpy(x).cuda(), rows, order)
+    cut = 2049
+    ya, sa = gt.fos_bank(torch.from_numpy(x[:, :cut].copy()).cuda(), rows, order)
+    yb, sb = gt.fos_bank(torch.from_numpy(x[:, cut:].copy()).cuda(), rows, order, sa)
+    y2 = torch.cat([ya, yb], dim=2)
+    for i, (b, a) in enumerate(coeffs):
+        for c in (0, 2):
+            y0, s0 = _fosfilter_scipy(b, a, order, x[c])
+            assert rel_l2(y[c, i].cpu().numpy(), y0) <= 1e-11, (order, i, c, rel_l2(y[c, i].cpu().numpy(), y0))
+            assert rel_l2(st[c, i].cpu().numpy(), s0) <= 1e-10
+            assert rel_l2(y2[c, i].cpu().numpy(), y0) <= 1e-11
+            assert rel_l2(sb[c, i].cpu().numpy(), s0) <= 1e-10
+
+
+def test_gammatone_complex_input_and_reanalyze(pfb):
+    """Complex signals are filtered like the reference's lfilter does (gammatone.py:232-236), not truncated to their
+    real part, and `reanalyze` (gammatone.py:318-321) sends every band through its own cascade again."""
+    gfb = pfb.GammatoneFilterbank(samplerate=16000, order=4, startband=-4, endband=4)
+    rng = np.random.default_rng(21)
+    n = 3000
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    res = list(gfb.analyze(x))
+    for i, (b, a) in enumerate(gfb._coeffs):
+        y0, s0 = _fosfilter_scipy(b, a, 4, x)
+        assert rel_l2(res[i][0], y0) <= 1e-12, (i, rel_l2(res[i][0], y0))
+        assert rel_l2(res[i][1], s0) <= 1e-11
+    xr = rng.standard_normal(n)
+    first = list(gfb.analyze(xr))
+    again = list(gfb.reanalyze([b for b, _ in first]))
+    assert len(again) == len(first)
+    for i, (b, a) in enumerate(gfb._coeffs):
+        y1, _ = _fosfilter_scipy(b, a, 4, xr)
+        y2, s2 = _fosfilter_scipy(b, a, 4, y1)
+        assert rel_l2(again[i][0], y2) <= 1e-11, (i, rel_l2(again[i][0], y2))
+        assert rel_l2(again[i][1], s2) <= 1e-10
+    # carried states through reanalyze, two blocks
+    cut = 1111
+    fa = list(gfb.analyze(xr[:cut]))
+    fb = list(gfb.analyze(xr[cut:], states=[s for _, s in fa]))
+    ra = list(gfb.reanalyze([b for b, _ in fa]))
+    rb = list(gfb.reanalyze([b for b, _ in fb], states=[s for _, s in ra]))
+    for i in range(len(first)):
+        assert rel_l2(np.concatenate([ra[i][0], rb[i][0]]), again[i][0]) <= 1e-11
