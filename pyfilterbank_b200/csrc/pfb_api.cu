@@ -609,6 +609,11 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     tp.nb_a = nb;
     tp.levels = levels, tp.lev_ld = lev_ld, tp.lev_off = lev_off, tp.ut = ut;
     tp.wide = wide ? 1 : 0;
+    {   // deep ring / two output tiles per band warp when at most two rounds of one CTA per SM cover the grid
+        const long long ctas = (long long)tp.CB * G * tp.NW;
+        bool deep = !wide && !levels && nb <= pfb::kTmaSmallBands && J == 1 && ctas <= 2LL * b->sm_count;
+        tp.deep = env_int("PFB_TMA_DEEP", deep ? 1 : 0) != 0 && !wide && !levels && nb <= pfb::kTmaSmallBands ? 1 : 0;
+    }
     if (weighted) {
         tp.weighted = 1;
         tp.wnz = ex->wnz;
@@ -903,7 +908,24 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         bool wide = same_arith && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
         if (ex) wide = false;               // the fused stages live in the 256-byte-fragment kernel
-        if (ex && ex->wnz) J = 1;           // the weighting recurrence is sequential in time: rows are whole channels
+        if (ex && ex->wnz) {
+            J = 1;                          // the weighting recurrence is sequential in time: rows are whole channels
+            // Bands per CTA: every band group repeats the prefilter, but few groups leave SMs idle or doubly loaded.
+            // Cost per SM ~ (CTAs it hosts) x (FP64 issue time of one CTA per sample: 17 DFMA per band and 4
+            // sections, 25 separately rounded operations of the prefilter); measured ordering in
+            // profiles/r02b_cfg5_sweep.jsonl.  PFB_TMA_NB overrides.
+            if (env_int("PFB_TMA_NB", 0) <= 0) {
+                const long long CBw = (C + 31) / 32;
+                const double band_cost = (arith64 ? 4.25 : 2.5) * b->K, w_cost = 25.0;
+                double best = 1e300;
+                for (int cand = 3; cand <= pfb::kTmaSmallBands; ++cand) {
+                    const int Gc = (b->B + cand - 1) / cand, nbc = (b->B + Gc - 1) / Gc;
+                    const double rounds = std::ceil((double)(CBw * Gc) / b->sm_count);
+                    const double cost = rounds * (nbc * band_cost + w_cost);
+                    if (cost < best) best = cost, nb = nbc, G = Gc;
+                }
+            }
+        }
         const int ttb = wide ? 2 * tt : tt;
         if (wide) {
             tma_bands(b, &nb, &G, true);

@@ -72,6 +72,7 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e != cudaSuccess) return (int)e;
     if (p.weighted && (NBMAX != kTmaSmallBands || p.J != 1 || p.wide)) return (int)cudaErrorInvalidValue;
+    if (p.deep && (NBMAX != kTmaSmallBands || p.wide)) return (int)cudaErrorInvalidValue;
     if (p.dec_band1 && (!PFB_HAS_DEC || p.levels || p.wide || p.weighted)) return (int)cudaErrorInvalidValue;
     static thread_local CoefTable<PFB_A> tab;
     for (int r = 0; r < p.B; ++r) {
@@ -114,7 +115,24 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             *launches += 1;
         }
         if (ev) cudaEventRecord(ev[2], s);
-        if (p.weighted) {
+        if (p.deep && !p.levels) {
+            // about one CTA per SM: deep input ring, two output tiles per band warp (small-band CTA shape only)
+            if constexpr (NBMAX == kTmaSmallBands) {
+                const int smem_d = (kTmaDeepStages + 2 * p.nb) * 2 * kTileBytes + 3 * kTmaDeepStages * 8;
+                auto launch_deep = [&](auto kern, int nthreads) -> cudaError_t {
+                    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
+                    if (e2 != cudaSuccess) return e2;
+                    kern<<<grid, nthreads, smem_d, s>>>(p, tab, xmap, ymap, ymap2);
+                    return cudaSuccess;
+                };
+                if (p.weighted) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, true, false>, threads + 32);
+#if PFB_HAS_DEC
+                else if (p.dec_band1) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, true>, threads);
+#endif
+                else e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, false>, threads);
+                if (e != cudaSuccess) return (int)e;
+            }
+        } else if (p.weighted) {
             // fused weighting prefilter: one more warp per CTA (small-band CTA shape only)
             if constexpr (NBMAX == kTmaSmallBands) {
                 if (p.levels) {

@@ -57,6 +57,7 @@ struct TmaParams {
     long long lev_ld, lev_off;
     int ut;
     int wide;             // output pass with 512-byte fragments (sos_tma_wide_kernel); L is then a multiple of 4 half rows
+    int deep;             // output pass with the deep ring / two output tiles per band warp (sos_tma_deep_kernel)
     // Fused SPL-weighting prefilter (WEIGHT kernels, splweighting.py:61-80): with one chunk per cascade a tile row is
     // a whole channel, so one extra warp runs the sequential transfer-function recurrence (scipy's operation
     // order, tf_step) in place on every input tile before the band warps read it -- the weighted signal never
@@ -316,8 +317,10 @@ __device__ __forceinline__ void weight_warp(const TmaParams &p, char *xs, uint64
 // faster but which need 16 KB output tiles per band warp); NS: input ring stages.
 // WEIGHT: one more warp (index nbw + 1) runs the weighting prefilter on every input tile (weight_warp) and the
 // band warps wait for ITS barrier; DEC: the band p.dec_band1 - 1 stores decimated samples through ymap2.
+// YB: output tiles per band warp (2: a tile's stores drain while the next tile is filtered into the other buffer --
+// the deep variant for launches with about one CTA per SM, where nothing else hides the store and load latencies).
 template <typename T, typename A, int K, int PASS, bool SCALED, int NH = 2, int NS = kTmaStages, bool WEIGHT = false,
-          bool DEC = false>
+          bool DEC = false, int YB = 1>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
                                         const CUtensorMap &ymap, const CUtensorMap &ymap2, char *smem, int cta, int ch0) {
     constexpr bool PASS_B = PASS != 0;
@@ -340,7 +343,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 
     char *xs = smem;                                          // [stages][2][tile]
     char *ys = smem + NS * kStageBytes;               // [nb][2][tile], output pass only
-    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb : 0) * kStageBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb * YB : 0) * kStageBytes);
     uint64_t *empty = full + NS;
     uint64_t *wfull = empty + NS;                             // WEIGHT kernels: weighting warp -> band warps
     uint64_t *in_bar = WEIGHT ? wfull : full;                 // what a band warp waits for
@@ -367,7 +370,10 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         t_first = nt - wt;
     }
 
-    if (warp == nbw) {
+    // warp roles: bands 0 .. nbw - 1, then (WEIGHT) the weighting warp, then the producer.  With 7 band warps the
+    // weighting warp (the heaviest FP64 instruction stream of the CTA) shares its SM sub-partition (warp index mod 4)
+    // with one band warp instead of two, and the nearly idle producer takes the crowded one.
+    if (warp == nbw + (WEIGHT ? 1 : 0)) {
         // ---------------- producer: stream the channel's input tiles into the ring ----------------
         if (lane == 0) {
             for (long long t = t_first; t < nt; ++t) {
@@ -384,7 +390,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
         return;
     }
-    if (WEIGHT && warp == nbw + 1) {
+    if (WEIGHT && warp == nbw) {
         // ---------------- weighting warp (PASS_B only, JR == 1: lane <-> channel CH * cb + lane) ----------------
         const int chn = p.CH * cb + lane;
         switch (p.wnz) {
@@ -434,7 +440,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         if (wt > nt) wt = nt;
         t_mine = (int)(nt - wt);
     }
-    char *ybuf = ys + warp * kStageBytes;
+    char *ybuf = ys + warp * YB * kStageBytes;
     char *yrow = ybuf + lane * kRowBytes;
 
     if (PASS == 2) {
@@ -467,11 +473,12 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait_warp(&in_bar[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            if (lane == 0) bulk_wait_read0();
+            const int yb = YB > 1 ? (int)(t % YB) * (int)kStageBytes : 0;
+            if (lane == 0) bulk_wait_read_upto(YB - 1);          // one bulk group per tile
             __syncwarp();
 #pragma unroll 1
             for (int h = 0; h < NH; ++h)
-                filter_half_dec<T, A, K, SCALED>(xrow + h * kTileBytes, yrow + (h >> 1) * kTileBytes, (h & 1) * 4, key,
+                filter_half_dec<T, A, K, SCALED>(xrow + h * kTileBytes, yrow + yb + (h >> 1) * kTileBytes, (h & 1) * 4, key,
                                                  p.dec_phase, c, wst);
             fence_proxy_async();
             __syncwarp();
@@ -479,7 +486,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 mbar_arrive(&empty[s]);
 #pragma unroll
                 for (int o = 0; o < NH / 2; ++o)
-                    tma_store_4d(&ymap2, ybuf + o * kTileBytes, (int)(t * (TT / 2) + o * TLEN), p.JR * w, 0, p.CH * cb);
+                    tma_store_4d(&ymap2, ybuf + yb + o * kTileBytes, (int)(t * (TT / 2) + o * TLEN), p.JR * w, 0, p.CH * cb);
                 bulk_commit();
             }
         }
@@ -498,11 +505,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             // stalls on instruction fetch; and with the warp-level waits above (real WARPSYNCs in the loop) every
             // fully unrolled variant lost 40-100 % (float64 cfg 2 output pass 15.8 vs 10.0 ms, cfg 3 21.9 vs 11.2 ms,
             // profiles/r01h_wait_variants.txt), while the rolled loop costs nothing measurable.
+            const int yb = YB > 1 ? (int)(t % YB) * (int)kStageBytes : 0;
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
-                if (lane == 0) bulk_wait_read_upto(NH - 1 - h);
+                // (YB buffers: the groups of the YB - 1 tiles in between may still be pending)
+                if (lane == 0) bulk_wait_read_upto((YB - 1) * NH + NH - 1 - h);
                 __syncwarp();
-                filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + h * kTileBytes, key, c, wst);
+                filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
             }
             fence_proxy_async();
             __syncwarp();
@@ -510,7 +519,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 mbar_arrive(&empty[s]);
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
-                    tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
+                    tma_store_4d(&ymap, ybuf + yb + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
                     bulk_commit();
                 }
             }
@@ -723,6 +732,19 @@ sos_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ Coef
                const __grid_constant__ CUtensorMap ymap2) {
     extern __shared__ __align__(1024) char smem[];
     tma_cta<T, A, K, PASS, SCALED, 2, kTmaStages, WEIGHT, DEC>(p, tab, xmap, ymap, ymap2, smem, blockIdx.x, 0);
+}
+
+// Output pass for launches with about one CTA per SM (one chunk per cascade and few (channel block, band group)
+// pairs: the many-channel configurations on a sharded bank): a deep input ring and two output tiles per band warp
+// hide the TMA load and store latencies that a second resident CTA would otherwise cover.
+constexpr int kTmaDeepStages = 8;
+template <typename T, typename A, int K, bool SCALED, bool WEIGHT, bool DEC>
+__global__ void __launch_bounds__((kTmaSmallBands + 1 + (WEIGHT ? 1 : 0)) * 32, 1)
+sos_tma_deep_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
+                    const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                    const __grid_constant__ CUtensorMap ymap2) {
+    extern __shared__ __align__(1024) char smem[];
+    tma_cta<T, A, K, 1, SCALED, 2, kTmaDeepStages, WEIGHT, DEC, 2>(p, tab, xmap, ymap, ymap2, smem, blockIdx.x, 0);
 }
 
 // Carry between the two passes: per cascade, s[0] = carried-in state, s[j+1] = P s[j] + z[j];

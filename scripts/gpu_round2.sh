@@ -36,8 +36,13 @@ fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-configs --no-f32 > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu list rc=$?"
+  mkdir -p /tmp/ncu
   for case in ${NCU_CASES:-cfg5 cfg3}; do
-    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"sos_tma|sos_hform|tf_seq" -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-6} -f \
-        -o $O/${TAG}_full_${case} python scripts/prof_fused.py $case > $O/${TAG}_ncu_${case}.log 2>&1; echo "ncu $case rc=$?"
+    # the reports stay on the box (gpurun_out/ is limited to 64 MiB): only their text summaries come back
+    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-sos_tma|sos_hform|tf_seq}" -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-6} -f \
+        -o /tmp/ncu/${TAG}_full_${case} python scripts/prof_fused.py $case > $O/${TAG}_ncu_${case}.log 2>&1; echo "ncu $case rc=$?"
+    python scripts/ncu_summary.py /tmp/ncu/${TAG}_full_${case}.ncu-rep > $O/${TAG}_full_${case}.txt 2>&1
+    sz=$(stat -c %s /tmp/ncu/${TAG}_full_${case}.ncu-rep 2>/dev/null || echo 0)
+    if [ "$sz" -lt 12000000 ] && [ -n "$NCU_KEEP" ]; then cp /tmp/ncu/${TAG}_full_${case}.ncu-rep $O/; fi
   done
 fi
