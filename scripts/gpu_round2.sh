@@ -42,6 +42,7 @@ if has ncu; then
     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-sos_tma|sos_hform|tf_seq}" -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-6} -f \
         -o /tmp/ncu/${TAG}_full_${case} python scripts/prof_fused.py $case > $O/${TAG}_ncu_${case}.log 2>&1; echo "ncu $case rc=$?"
     python scripts/ncu_summary.py /tmp/ncu/${TAG}_full_${case}.ncu-rep > $O/${TAG}_full_${case}.txt 2>&1
+    python scripts/ncu_hot.py /tmp/ncu/${TAG}_full_${case}.ncu-rep ${NCU_TOP:-45} > $O/${TAG}_hot_${case}.txt 2>&1
     sz=$(stat -c %s /tmp/ncu/${TAG}_full_${case}.ncu-rep 2>/dev/null || echo 0)
     if [ "$sz" -lt 12000000 ] && [ -n "$NCU_KEEP" ]; then cp /tmp/ncu/${TAG}_full_${case}.ncu-rep $O/; fi
   done
