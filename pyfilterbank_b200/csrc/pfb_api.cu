@@ -644,11 +644,33 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
         for (cudaEvent_t &e : ev) e = b->tev_new();
     int launches = 0;
     const double *ch = b->coef_host.data();
+#if PFB_WARP_PROF
+    static unsigned long long *prof_dev = nullptr;
+    if (env_int("PFB_WARP_PROF", 0)) {
+        if (!prof_dev) cudaMalloc(&prof_dev, 16 * 8 * 8);
+        cudaMemsetAsync(prof_dev, 0, 16 * 8 * 8, stream);
+        tp.prof = prof_dev;
+    }
+#endif
     int err = dtype == PFB_F64 ? pfb::launch_tma_dd(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3)
               : arith64       ? pfb::launch_tma_fd(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3)
                               : pfb::launch_tma_ff(tp, b->K, ch, xmap, ymap, ymap2, stream, &launches, timed ? ev : nullptr, 3);
     if (wz_copy) cudaFreeAsync(wz_copy, stream);
     if (err != 0) return fail(PFB_ERR_CUDA, "TMA kernel launch failed: %s", cudaGetErrorString((cudaError_t)err));
+#if PFB_WARP_PROF
+    if (tp.prof) {   // experiment builds: clocks per warp role of the output pass, per CTA and tile step
+        unsigned long long h[16 * 8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
+        const double ctas = (double)tp.CB * G * tp.NW, steps = (double)(Lt / tt), d = ctas * steps;
+        fprintf(stderr, "[warp prof] J=%d nb=%d G=%d ctas=%.0f tile steps=%.0f; clocks per tile step and CTA:\n"
+                        "           wait-in    arith  out-wait    fence   arrive+store   total\n", J, nb, G, ctas, steps);
+        for (int w = 0; w < 16; ++w)
+            if (h[w * 8 + 3])
+                fprintf(stderr, "  warp %2d %8.0f %8.0f %8.0f %8.0f %8.0f %12.0f%s\n", w, h[w * 8] / d, h[w * 8 + 1] / d, h[w * 8 + 2] / d,
+                        h[w * 8 + 4] / d, h[w * 8 + 5] / d, h[w * 8 + 3] / d, w == 15 ? " (weighting)" : "");
+    }
+#endif
     if (timed) {
         b->trecs.push_back({ev[0], ev[1], 0});
         b->trecs.push_back({ev[1], ev[2], 1});
@@ -910,20 +932,13 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         if (ex) wide = false;               // the fused stages live in the 256-byte-fragment kernel
         if (ex && ex->wnz) {
             J = 1;                          // the weighting recurrence is sequential in time: rows are whole channels
-            // Bands per CTA: every band group repeats the prefilter, but few groups leave SMs idle or doubly loaded.
-            // Cost per SM ~ (CTAs it hosts) x (FP64 issue time of one CTA per sample: 17 DFMA per band and 4
-            // sections, 25 separately rounded operations of the prefilter); measured ordering in
-            // profiles/r02b_cfg5_sweep.jsonl.  PFB_TMA_NB overrides.
-            if (env_int("PFB_TMA_NB", 0) <= 0) {
-                const long long CBw = (C + 31) / 32;
-                const double band_cost = (arith64 ? 4.25 : 2.5) * b->K, w_cost = 25.0;
-                double best = 1e300;
-                for (int cand = 3; cand <= pfb::kTmaSmallBands; ++cand) {
-                    const int Gc = (b->B + cand - 1) / cand, nbc = (b->B + Gc - 1) / Gc;
-                    const double rounds = std::ceil((double)(CBw * Gc) / b->sm_count);
-                    const double cost = rounds * (nbc * band_cost + w_cost);
-                    if (cost < best) best = cost, nb = nbc, G = Gc;
-                }
+            // Bands per CTA (sos_tma_weighted_kernel: 9 band warps on three SM sub-partitions, the weighting warp alone
+            // on the fourth, one CTA per SM): as many as fit, in equal groups -- every group repeats the prefilter, and
+            // three band warps per sub-partition reach the FP64 issue limit.  PFB_TMA_NB overrides.
+            {
+                const int nbmax = std::max(1, std::min(env_int("PFB_TMA_NB", pfb::kTmaWeightBands), pfb::kTmaWeightBands));
+                G = (b->B + nbmax - 1) / nbmax;
+                nb = (b->B + G - 1) / G;
             }
         }
         const int ttb = wide ? 2 * tt : tt;
@@ -1396,8 +1411,7 @@ int pfb_bank_filter_weighted(pfb_bank *b, int dtype, const void *x, int64_t ldx,
     ex.wz = wz;
     // Fused pass: one chunk per cascade, so it pays when (channel blocks x band groups) fill a good part of the
     // machine; few channels take the weighting kernel and the time-chunked bank.  PFB_WEIGHT_FUSED=0/1 overrides.
-    int nbw, G;
-    tma_bands(b, &nbw, &G, false);
+    const int G = (b->B + pfb::kTmaWeightBands - 1) / pfb::kTmaWeightBands;
     bool fused = !(flags & PFB_EXACT) && nz >= 4 && nz <= 6 && (long long)((C + 31) / 32) * G * 2 >= b->sm_count;
     fused = env_int("PFB_WEIGHT_FUSED", fused ? 1 : 0) != 0;
     long long done = 0;

@@ -170,6 +170,7 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
             }
         }
         if (PASS_B) fence_proxy_async();
+        else asm volatile("fence.acq_rel.cta;\n" ::: "memory");   // pre-pass: see stage_release_after_reads (pfb_tma.cuh)
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[s]);

@@ -59,22 +59,9 @@ static int run_scan(const SosParams &p, int warps, const double *coef_host, int 
                      : run_scan_a<K, false>(p, warps, coef_host, rows, C, s, launches);
 }
 
-template <int K, int NBMAX, bool SCALED>
-static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
-                      const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
-    auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, 0, NBMAX, SCALED>;
-    auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED>;
-    auto kern_l = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED>;
-    const int smem_a = kTmaStages * 2 * kTileBytes + 3 * kTmaStages * 8;
-    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 3 * kTmaStages * 8;
-    cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
-    if (e != cudaSuccess) return (int)e;
-    if (p.weighted && (NBMAX != kTmaSmallBands || p.J != 1 || p.wide)) return (int)cudaErrorInvalidValue;
-    if (p.deep && (NBMAX != kTmaSmallBands || p.wide)) return (int)cudaErrorInvalidValue;
-    if (p.dec_band1 && (!PFB_HAS_DEC || p.levels || p.wide || p.weighted)) return (int)cudaErrorInvalidValue;
-    static thread_local CoefTable<PFB_A> tab;
+// Coefficient table of the TMA kernels (kernel parameter block -> uniform registers): [band][section][5]
+template <int K, bool SCALED>
+static void fill_tma_table(const TmaParams &p, const double *coef_host, CoefTable<PFB_A> &tab) {
     for (int r = 0; r < p.B; ++r) {
         double total_gain = 1.0;
         for (int k = 0; k < K; ++k) {
@@ -88,6 +75,60 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
         }
         if (SCALED) tab.c[r * K][0] = (PFB_A)total_gain;
     }
+}
+
+// Fused weighting prefilter + bank (sos_tma_weighted_kernel): one chunk per cascade, <= 9 bands per CTA, one launch.
+template <int K, bool SCALED>
+static int run_tma_weighted(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                            cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    if (p.J != 1 || p.nb > kTmaWeightBands || p.wide || p.deep || p.dec_band1) return (int)cudaErrorInvalidValue;
+    static thread_local CoefTable<PFB_A> tab;
+    fill_tma_table<K, SCALED>(p, coef_host, tab);
+    const unsigned grid = (unsigned)p.CB * (unsigned)p.G * (unsigned)p.NW;
+    const int last_band_warp = (p.nb - 1) + (p.nb - 1) / 3;              // band slot -> warp index (every fourth is skipped)
+    const int threads = 32 * (last_band_warp + 1 > 8 ? last_band_warp + 1 : 8);
+    const int smem_in = kTmaWeightStages * 2 * kTileBytes + 3 * kTmaWeightStages * 8;
+    if (ev && (phases & 1)) {   // a single chunk per cascade needs no pre-pass
+        cudaEventRecord(ev[0], s);
+        cudaEventRecord(ev[1], s);
+    }
+    if (!(phases & 2)) return 0;
+    if (ev) cudaEventRecord(ev[2], s);
+    cudaError_t e;
+    if (p.levels) {
+        auto kern = sos_tma_weighted_kernel<PFB_T, PFB_A, K, 2, SCALED>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_in);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, threads, smem_in, s>>>(p, tab, xmap, ymap);
+    } else {
+        const int smem = smem_in + 2 * p.nb * 2 * kTileBytes;
+        auto kern = sos_tma_weighted_kernel<PFB_T, PFB_A, K, 1, SCALED>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, threads, smem, s>>>(p, tab, xmap, ymap);
+    }
+    if (ev) cudaEventRecord(ev[3], s);
+    *launches += 1;
+    return (int)cudaGetLastError();
+}
+
+template <int K, int NBMAX, bool SCALED>
+static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
+                      const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    auto kern_a = sos_tma_kernel<PFB_T, PFB_A, K, 0, NBMAX, SCALED>;
+    auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED>;
+    auto kern_l = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED>;
+    const int smem_a = kTmaStages * 2 * kTileBytes + 3 * kTmaStages * 8;
+    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 3 * kTmaStages * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
+    if (e != cudaSuccess) return (int)e;
+    if (p.weighted) return (int)cudaErrorInvalidValue;   // run_tma_weighted
+    if (p.deep && (NBMAX != kTmaSmallBands || p.wide)) return (int)cudaErrorInvalidValue;
+    if (p.dec_band1 && (!PFB_HAS_DEC || p.levels || p.wide || p.weighted)) return (int)cudaErrorInvalidValue;
+    static thread_local CoefTable<PFB_A> tab;
+    fill_tma_table<K, SCALED>(p, coef_host, tab);
     constexpr int S = 2 * K;
     constexpr int LPC = S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16;
     const unsigned grid = (unsigned)p.CB * (unsigned)p.G * (unsigned)p.NW;
@@ -125,27 +166,12 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
                     kern<<<grid, nthreads, smem_d, s>>>(p, tab, xmap, ymap, ymap2);
                     return cudaSuccess;
                 };
-                if (p.weighted) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, true, false>, threads + 32);
 #if PFB_HAS_DEC
-                else if (p.dec_band1) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, true>, threads);
+                if (p.dec_band1) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, true>, threads);
+                else
 #endif
-                else e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, false>, threads);
+                    e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, false>, threads);
                 if (e != cudaSuccess) return (int)e;
-            }
-        } else if (p.weighted) {
-            // fused weighting prefilter: one more warp per CTA (small-band CTA shape only)
-            if constexpr (NBMAX == kTmaSmallBands) {
-                if (p.levels) {
-                    auto kern_lw = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED, true, false>;
-                    e = cudaFuncSetAttribute(kern_lw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
-                    if (e != cudaSuccess) return (int)e;
-                    kern_lw<<<grid, threads + 32, smem_a, s>>>(p, tab, xmap, ymap, ymap2);
-                } else {
-                    auto kern_bw = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED, true, false>;
-                    e = cudaFuncSetAttribute(kern_bw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
-                    if (e != cudaSuccess) return (int)e;
-                    kern_bw<<<grid, threads + 32, smem_b, s>>>(p, tab, xmap, ymap, ymap2);
-                }
             }
         } else if (p.dec_band1) {
 #if PFB_HAS_DEC
@@ -181,6 +207,12 @@ static int run_tma_n(const TmaParams &p, const double *coef_host, const CUtensor
 template <int K>
 static int run_tma(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
                    const CUtensorMap &ymap2, cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
+    if (p.weighted) {
+#if PFB_HAS_SCALED
+        if (p.gains) return run_tma_weighted<K, true>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+#endif
+        return run_tma_weighted<K, false>(p, coef_host, xmap, ymap, s, launches, ev, phases);
+    }
     return p.nb <= kTmaSmallBands ? run_tma_n<K, kTmaSmallBands>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases)
                                   : run_tma_n<K, kTmaMaxBands>(p, coef_host, xmap, ymap, ymap2, s, launches, ev, phases);
 }

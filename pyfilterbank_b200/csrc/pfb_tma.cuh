@@ -72,7 +72,24 @@ struct TmaParams {
     // in dec_states [C][Ktot][2]; the states array then holds Bs = B - 1 bands (Bs == 0 means B).
     int dec_band1, dec_phase, Bs;
     void *dec_states;
+    // PFB_WARP_PROF builds only: clocks per warp role, [warp index][0 wait for input, 1 arithmetic, 2 wait for the
+    // output buffer, 3 total, 4 proxy fence + warp sync, 5 barrier arrive + store issue], summed over CTAs (lane 0's clock64)
+    unsigned long long *prof;
 };
+
+#ifndef PFB_WARP_PROF
+#define PFB_WARP_PROF 0
+#endif
+#if PFB_WARP_PROF
+#define PROF_DECL long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long prof_c = clock64(); const long long prof_0 = prof_c
+#define PROF_LAP(i) do { const long long prof_n = clock64(); prof_t[i] += prof_n - prof_c; prof_c = prof_n; } while (0)
+#define PROF_END(p, warp, lane) do { if ((p).prof && (lane) == 0) { prof_t[3] = clock64() - prof_0; \
+    for (int prof_i = 0; prof_i < 8; ++prof_i) atomicAdd((p).prof + (warp) * 8 + prof_i, (unsigned long long)prof_t[prof_i]); } } while (0)
+#else
+#define PROF_DECL do {} while (0)
+#define PROF_LAP(i) do {} while (0)
+#define PROF_END(p, warp, lane) do {} while (0)
+#endif
 
 // States (w1, w2 per section, sections k0..) of cascade (channel, band).
 template <typename A>
@@ -92,48 +109,86 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+// Release of an input stage by a warp that only READ it (pre-pass and band-level kernels; the output pass has a proxy
+// fence between its loads and the release anyway).  Every lane fences first: a lane's loads of the stage must have
+// been performed before lane 0's arrive lets the producer refill it.  Without it ptxas schedules the arrive right behind
+// the ISSUE of the last LDS and the refill can overtake loads still queued in the SM's shared-memory pipeline.
+__device__ __forceinline__ void stage_release_after_reads(uint64_t *bar, int lane) {
+    asm volatile("fence.acq_rel.cta;\n" ::: "memory");
+    if (lane == 0) mbar_arrive(bar);
+}
+// One non-blocking phase test (no branch inside the asm: the caller decides what to do with the result).
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
 }
-// Wait of a whole consumer warp: one lane polls, the warp re-converges on __syncwarp(), then every lane performs
-// its own (immediately successful) wait so that each of them has acquired the phase.
-// Polling with all 32 lanes in the spin loop of mbar_wait() turned out NOT to be equivalent.  Measured
-// (scripts/ubench/fos_race.cu, profiles/r01h_fos_race.txt): with 3-4 CTAs resident per SM the gammatone pre-pass
-// gave 2-10 k of 1 M chunk states that differed between runs of the same launch; with one CTA per SM, or with this
-// wait, none.  ptxas compiles the all-lane loop as if the warp were converged behind it (every later __syncwarp()
-// disappears from the SASS), so lanes that leave the loop apart are never joined again and the stragglers read a
-// stage after lane 0 has already released it to the producer -- the most likely mechanism; the fix is the
-// measured part.
+// Wait of a single thread (the producer lane).  The loop is C++, not a branch inside the asm: ptxas must see the
+// control flow, or it treats the code behind a single-lane spin as converged (see mbar_wait_warp).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// Wait of a whole consumer warp: every lane tests the phase (no branch inside the asm) and a warp vote ends the loop
+// uniformly, so the warp stays one converged group and every lane has itself observed (acquired) the phase.
+//
+// History, all measured.
+// (0) All 32 lanes spinning in a branch-inside-asm loop: ptxas compiles the loop as if the warp were converged behind
+//     it and removes every later __syncwarp(); with 3-4 CTAs per SM the gammatone pre-pass then gave chunk states that
+//     differed between runs of the same launch (scripts/ubench/fos_race.cu, profiles/r01h_fos_race.txt).
+// (2) Lane 0 polls, __syncwarp(), every lane waits once more (rounds 1h-2a): reproducible, but the warp leaves that
+//     sequence SPLIT -- lane 0 and lanes 1-31 run on as two groups until the next __syncwarp() and everything in
+//     between is issued twice.  Clocks of lane 0 and lane 31 of the weighting warp (profiles/r02l_warp_prof.txt):
+//     both spend 2160 clocks per tile in the arithmetic, one after the other.  That was the unexplained factor 2 of
+//     round 1 (recurrence pre-pass 6.5 -> 14.0 ms, band levels, every fully unrolled output pass 40-100 % slower).
+// (4) = (2) plus a closing __syncwarp(): reproducible and converged, but 10-40 % slower than (3) on the kernels with one
+//     CTA per SM (cfg 5 18.2 / 16.1 ms against 14.4 / 9.3 ms, gammatone cfg 4 20.5 against 18.2 ms; profiles/r02o).
+// (3) This form.  ptxas again removes the __syncwarp()s (the warp IS converged now), which exposed what the race of
+//     (0) really was: in the pre-pass kernels nothing orders the release of a stage (lane 0's mbarrier.arrive) behind the
+//     shared-memory LOADS of the tile -- ptxas schedules the arrive right behind the last LDS *issue*, the loads of 28
+//     warps queue up for hundreds of clocks, and the producer's refill lands first.  Experiments (profiles/
+//     r02p_wait_experiments.txt): delays, proxy fences, more try_waits and a release by every lane change nothing; the
+//     pre-pass alone in form (4) removes the effect; so does a fence.acq_rel.cta of every lane in front of the arrive
+//     (stage_release_after_reads), which is what every release without a proxy fence in front of it now does.
 #ifndef PFB_WAIT_MODE
-#define PFB_WAIT_MODE 2
+#define PFB_WAIT_MODE 3
 #endif
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, unsigned parity, int lane) {
 #if PFB_WAIT_MODE == 0
     mbar_wait(bar, parity);
+#elif PFB_WAIT_MODE == 3
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    }
 #else
     if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
-#if PFB_WAIT_MODE == 2
+#if PFB_WAIT_MODE >= 2
     mbar_wait(bar, parity);
+#endif
+#if PFB_WAIT_MODE == 4
+    __syncwarp();
 #endif
 #endif
 }
 // Tiles that are only released (not read): lane 0 waits and arrives alone, the rest of the warp does nothing.
 __device__ __forceinline__ void mbar_skip_tile(uint64_t *full_bar, uint64_t *empty_bar, unsigned parity, int lane) {
+#if PFB_WAIT_MODE == 3
+    mbar_wait_warp(full_bar, parity, lane);          // the whole warp, converged; one lane releases
+    if (lane == 0) mbar_arrive(empty_bar);
+#else
     if (lane == 0) {
         mbar_wait(full_bar, parity);
         mbar_arrive(empty_bar);
     }
+#endif
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
@@ -178,6 +233,53 @@ __device__ __forceinline__ A scaled_step(A x, const A *c, A &w1, A &w2) {
     return y;
 }
 
+// One section step of the arithmetic the TMA kernels run (gain-normalised or plain FMA form).
+template <typename A, bool SCALED>
+__device__ __forceinline__ A section_step(A x, const A *c, A &w1, A &w2) {
+    return SCALED ? scaled_step<A>(x, c, w1, w2) : Biquad<A, false>::step(x, c, w1, w2);
+}
+
+// All samples of a 128-byte half row (e[0 .. NS), in registers) through the K sections, in place, in WAVEFRONT
+// order: step d runs section k on sample d - k for every k.  The K updates of one step are independent of each other
+// (section k reads what section k - 1 produced one step earlier), so a single warp carries K-fold instruction-level
+// parallelism where the sample-by-sample order is one dependent chain of 4 K operations per sample.  Same operations,
+// same results.  Measured (scripts/ubench/smsp_map.cu, profiles/r02g_smsp_map.txt): with the three band warps per
+// SM sub-partition that the 11/12-warp CTAs have, 113 instead of 142 clocks per sample, i.e. the FP64 issue limit.
+// `out(m, y)` receives the finished sample m.
+#ifndef PFB_WAVE
+#define PFB_WAVE 1
+#endif
+#ifndef PFB_W_ROLLED
+#define PFB_W_ROLLED 0
+#endif
+template <typename T, typename A, int K, bool SCALED, int NS, typename Out>
+__device__ __forceinline__ void cascade_wave(const T *e, const A (&c)[K][5], A (&w)[K][2], Out out) {
+#if PFB_WAVE
+    A v[K + 1];
+#pragma unroll
+    for (int d = 0; d < NS + K - 1; ++d) {
+#pragma unroll
+        for (int k = K - 1; k >= 0; --k) {      // descending: section k + 1 has consumed v[k + 1] before k rewrites it
+            const int m = d - k;
+            if (m >= 0 && m < NS) {
+                const A xin = k == 0 ? (A)e[m] : v[k];
+                const A y = section_step<A, SCALED>(xin, c[k], w[k][0], w[k][1]);
+                if (k == K - 1) out(m, SCALED ? y * c[0][0] : y);
+                else v[k + 1] = y;
+            }
+        }
+    }
+#else
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+        A s = (A)e[m];
+#pragma unroll
+        for (int k = 0; k < K; ++k) s = section_step<A, SCALED>(s, c[k], w[k][0], w[k][1]);
+        out(m, SCALED ? s * c[0][0] : s);
+    }
+#endif
+}
+
 // Filter one 128-byte half tile: x row read from the shared input tile.  MODE 1: result written to the warp's
 // own output tile (same swizzled layout); MODE 0: pre-pass, nothing is written; MODE 2: the squares of the
 // (output-type rounded) results are added to `acc` (band-level epilogue).
@@ -187,29 +289,21 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
     constexpr bool STORE = MODE == 1;
     using V = typename Vec16<T>::type;
     constexpr int EPV = Vec16<T>::N;
-    constexpr int kBatch = PFB_ROW_BATCH;
+    // float64 arithmetic on float32 rows: two wavefronts of 16 samples (a 32-sample one holds too many doubles)
+    constexpr int kBatch = (sizeof(T) == 4 && sizeof(A) == 8) ? kVecPerRow / 2 : kVecPerRow;
 #pragma unroll
     for (int v0 = 0; v0 < kVecPerRow; v0 += kBatch) {
         V in[kBatch];
 #pragma unroll
         for (int v = 0; v < kBatch; ++v) in[v] = *reinterpret_cast<const V *>(xrow + (((v0 + v) ^ key) << 4));
-#pragma unroll
-        for (int v = 0; v < kBatch; ++v) {
-            T *e = reinterpret_cast<T *>(&in[v]);
-#pragma unroll
-            for (int i = 0; i < EPV; ++i) {
-                A s = (A)e[i];
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    s = SCALED ? scaled_step<A>(s, c[k], w[k][0], w[k][1]) : Biquad<A, false>::step(s, c[k], w[k][0], w[k][1]);
-                if (SCALED) s *= c[0][0];
-                e[i] = (T)s;
-                if (MODE == 2) {
-                    const A r = (A)e[i];
-                    *acc = fma(r, r, *acc);
-                }
+        T *e = reinterpret_cast<T *>(&in[0]);
+        cascade_wave<T, A, K, SCALED, kBatch * EPV>(e, c, w, [&](int m, A y) {
+            e[m] = (T)y;
+            if (MODE == 2) {
+                const A r = (A)e[m];
+                *acc = fma(r, r, *acc);
             }
-        }
+        });
         if (STORE) {
 #pragma unroll
             for (int v = 0; v < kBatch; ++v) *reinterpret_cast<V *>(yrow + (((v0 + v) ^ key) << 4)) = in[v];
@@ -226,38 +320,22 @@ __device__ __forceinline__ void filter_half_dec(const char *xrow, char *yrow, in
                                                 A (&w)[K][2]) {
     using V = typename Vec16<T>::type;
     constexpr int EPV = Vec16<T>::N;
-    constexpr int kBatch = PFB_ROW_BATCH;
-    static_assert(kBatch % 2 == 0, "two input vectors fill one output vector");
+    V in[kVecPerRow];
 #pragma unroll
-    for (int v0 = 0; v0 < kVecPerRow; v0 += kBatch) {
-        V in[kBatch];
+    for (int v = 0; v < kVecPerRow; ++v) in[v] = *reinterpret_cast<const V *>(xrow + ((v ^ key) << 4));
+    T *e = reinterpret_cast<T *>(&in[0]);
+    cascade_wave<T, A, K, SCALED, kVecPerRow * EPV>(e, c, w, [&](int m, A y) { e[m] = (T)y; });
 #pragma unroll
-        for (int v = 0; v < kBatch; ++v) in[v] = *reinterpret_cast<const V *>(xrow + (((v0 + v) ^ key) << 4));
+    for (int v = 0; v < kVecPerRow; v += 2) {
+        V o;
+        T *oe = reinterpret_cast<T *>(&o);
+        const T *e0 = reinterpret_cast<const T *>(&in[v]), *e1 = reinterpret_cast<const T *>(&in[v + 1]);
 #pragma unroll
-        for (int v = 0; v < kBatch; ++v) {
-            T *e = reinterpret_cast<T *>(&in[v]);
-#pragma unroll
-            for (int i = 0; i < EPV; ++i) {
-                A s = (A)e[i];
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    s = SCALED ? scaled_step<A>(s, c[k], w[k][0], w[k][1]) : Biquad<A, false>::step(s, c[k], w[k][0], w[k][1]);
-                if (SCALED) s *= c[0][0];
-                e[i] = (T)s;
-            }
+        for (int i = 0; i < EPV / 2; ++i) {
+            oe[i] = phase ? e0[2 * i + 1] : e0[2 * i];
+            oe[EPV / 2 + i] = phase ? e1[2 * i + 1] : e1[2 * i];
         }
-#pragma unroll
-        for (int v = 0; v < kBatch; v += 2) {
-            V o;
-            T *oe = reinterpret_cast<T *>(&o);
-            const T *e0 = reinterpret_cast<const T *>(&in[v]), *e1 = reinterpret_cast<const T *>(&in[v + 1]);
-#pragma unroll
-            for (int i = 0; i < EPV / 2; ++i) {
-                oe[i] = phase ? e0[2 * i + 1] : e0[2 * i];
-                oe[EPV / 2 + i] = phase ? e1[2 * i + 1] : e1[2 * i];
-            }
-            *reinterpret_cast<V *>(yrow + (((c0 + (v0 + v) / 2) ^ key) << 4)) = o;
-        }
+        *reinterpret_cast<V *>(yrow + (((c0 + v / 2) ^ key) << 4)) = o;
     }
 }
 
@@ -267,6 +345,32 @@ template <typename T, int NZ>
 __device__ __forceinline__ void weight_half(char *row, int key, const double (&b)[8], const double (&a)[8], double (&z)[NZ]) {
     using V = typename Vec16<T>::type;
     constexpr int EPV = Vec16<T>::N;
+#if PFB_W_ROLLED
+    // Rolled loop over groups of four samples (100 FP64 instructions, 1.6 KB of code), the next group loaded ahead:
+    // an experiment against instruction-fetch stalls of the lone weighting warp; measured slower than the unrolled
+    // half row (19.9 against 17.6 ms on cfg 5, profiles/r02l_warp_prof.txt).
+    constexpr int VG = 4 / EPV;                  // 16-byte vectors per group: 2 (float64), 1 (float32)
+    V cur[VG], nxt[VG];
+#pragma unroll
+    for (int v = 0; v < VG; ++v) cur[v] = *reinterpret_cast<const V *>(row + ((v ^ key) << 4));
+#pragma unroll 1
+    for (int i = 0; i < kVecPerRow; i += VG) {
+        const int in = i + VG < kVecPerRow ? i + VG : i;
+#pragma unroll
+        for (int v = 0; v < VG; ++v) nxt[v] = *reinterpret_cast<const V *>(row + (((in + v) ^ key) << 4));
+#pragma unroll
+        for (int v = 0; v < VG; ++v) {
+            T *e = reinterpret_cast<T *>(&cur[v]);
+#pragma unroll
+            for (int j = 0; j < EPV; ++j) e[j] = (T)tf_step<NZ>((double)e[j], b, a, z);
+        }
+#pragma unroll
+        for (int v = 0; v < VG; ++v) {
+            *reinterpret_cast<V *>(row + (((i + v) ^ key) << 4)) = cur[v];
+            cur[v] = nxt[v];
+        }
+    }
+#else
     V v[kVecPerRow];
 #pragma unroll
     for (int i = 0; i < kVecPerRow; ++i) v[i] = *reinterpret_cast<const V *>(row + ((i ^ key) << 4));
@@ -278,6 +382,7 @@ __device__ __forceinline__ void weight_half(char *row, int key, const double (&b
     }
 #pragma unroll
     for (int i = 0; i < kVecPerRow; ++i) *reinterpret_cast<V *>(row + ((i ^ key) << 4)) = v[i];
+#endif
 }
 
 // The weighting warp of a WEIGHT kernel: lane <-> tile row <-> channel (one chunk per cascade).  Waits for the
@@ -293,16 +398,25 @@ __device__ __forceinline__ void weight_warp(const TmaParams &p, char *xs, uint64
     for (int k = 0; k < 8; ++k) { b[k] = p.wb[k]; a[k] = p.wa[k]; }
 #pragma unroll
     for (int k = 0; k < NZ; ++k) z[k] = ok ? p.wz_in[(size_t)chn * 8 + k] : 0.0;
+    PROF_DECL;
     for (long long t = 0; t < nt; ++t) {
         const int s = (int)(t % NS);
         mbar_wait_warp(&full[s], (unsigned)((t / NS) & 1), lane);
+        PROF_LAP(0);
         char *xrow = xs + s * kStageBytes + lane * kRowBytes;
 #pragma unroll 1
         for (int h = 0; h < NH; ++h) weight_half<T, NZ>(xrow + h * kTileBytes, key, b, a, z);
+        PROF_LAP(1);
+#if !PFB_W_NOFENCE
         fence_proxy_async();      // the stage is refilled through the async proxy after the band warps release it
+#endif
         __syncwarp();
+        PROF_LAP(4);
         if (lane == 0) mbar_arrive(&wfull[s]);
+        PROF_LAP(5);
     }
+    PROF_END(p, 15, lane);
+    PROF_END(p, 14, lane - 31);      // lane 31's clocks: a diverged warp shows up as different laps
     if (ok && write_back) {
 #pragma unroll
         for (int k = 0; k < NZ; ++k) p.wz[(size_t)chn * NZ + k] = z[k];
@@ -370,10 +484,18 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         t_first = nt - wt;
     }
 
-    // warp roles: bands 0 .. nbw - 1, then (WEIGHT) the weighting warp, then the producer.  With 7 band warps the
-    // weighting warp (the heaviest FP64 instruction stream of the CTA) shares its SM sub-partition (warp index mod 4)
-    // with one band warp instead of two, and the nearly idle producer takes the crowded one.
-    if (warp == nbw + (WEIGHT ? 1 : 0)) {
+    // Warp roles.  Plain kernels: bands 0 .. nbw - 1, then the producer.
+    // WEIGHT kernels spread the roles over the SM's four sub-partitions (a warp issues on sub-partition
+    // warp index mod 4, scripts/ubench/smsp_map.cu): warp 3 is the weighting warp, warp 7 the producer, warp 11 idles,
+    // the band warps are the others (0 1 2, 4 5 6, 8 9 10 -> at most 9 bands).  The prefilter is one sequential FP64
+    // instruction stream per CTA (25 separately rounded operations per sample, 56 issue clocks alone): sharing its
+    // sub-partition with band warps (and their polling lanes) made it the slowest stage of the pipeline by 2-3x
+    // (profiles/r02j_warp_prof.txt: 184 clocks per sample against 77 in isolation).
+    constexpr int kWeightWarp = 3, kSpreadProducer = 7;
+    const int prod_warp = WEIGHT ? kSpreadProducer : nbw;
+    if (WEIGHT && (warp & 3) == 3 && warp != kWeightWarp && warp != kSpreadProducer) return;
+    const int slot = WEIGHT ? warp - (warp >> 2) : warp;            // band slot of a band warp
+    if (warp == prod_warp) {
         // ---------------- producer: stream the channel's input tiles into the ring ----------------
         if (lane == 0) {
             for (long long t = t_first; t < nt; ++t) {
@@ -390,7 +512,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
         return;
     }
-    if (WEIGHT && warp == nbw) {
+    if (WEIGHT && warp == kWeightWarp) {
         // ---------------- weighting warp (PASS_B only, JR == 1: lane <-> channel CH * cb + lane) ----------------
         const int chn = p.CH * cb + lane;
         switch (p.wnz) {
@@ -400,10 +522,10 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
         return;
     }
-    if (warp >= nb_here) return;
+    if (slot >= nb_here) return;
 
     // ---------------- consumers: one band per warp, one (channel, chunk) row per lane ----------------
-    const int band = b0 + warp;
+    const int band = b0 + slot;
     const int chn = p.CH * cb + lane / p.JR;
     const bool row_ok = chn < p.C;                // channel blocks may be ragged: TMA clips the tile, lanes idle
     const int q = (row_ok ? chn : 0) * p.B + band;
@@ -412,7 +534,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     A c[K][5], wst[K][2];
     // a second, independently reduced copy of the band index that is used for nothing but the
     // coefficient table, so its users stay on the uniform datapath
-    const int band_u = b0 + __reduce_min_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int warp_u = __reduce_min_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int band_u = b0 + (WEIGHT ? warp_u - (warp_u >> 2) : warp_u);
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -440,7 +563,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         if (wt > nt) wt = nt;
         t_mine = (int)(nt - wt);
     }
-    char *ybuf = ys + warp * YB * kStageBytes;
+    char *ybuf = ys + slot * YB * kStageBytes;
     char *yrow = ybuf + lane * kRowBytes;
 
     if (PASS == 2) {
@@ -456,7 +579,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll 1   // rolled like the output pass (float32 levels: 13.1 ms unrolled, see profiles/r01h_wait_variants.txt)
             for (int h = 0; h < NH; ++h) filter_half<T, A, K, 2, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst, &acc);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            stage_release_after_reads(&empty[s], lane);
             acc_unit += (double)acc;
             if (++tcount == p.ut) {
                 if (row_ok) *lev = acc_unit;
@@ -491,10 +614,12 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             }
         }
     } else if (PASS_B) {
+        PROF_DECL;
         for (long long t = 0; t < nt; ++t) {
             const int s = (int)(t % NS);
             const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait_warp(&in_bar[s], ph, lane);
+            PROF_LAP(0);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
             // The tile's NH half rows are stored together at the end of the tile: a row's fragment must reach HBM as
             // one burst (storing each 128-byte half as soon as it is filtered dropped the write efficiency from ~5.0
@@ -511,10 +636,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 // (YB buffers: the groups of the YB - 1 tiles in between may still be pending)
                 if (lane == 0) bulk_wait_read_upto((YB - 1) * NH + NH - 1 - h);
                 __syncwarp();
+                PROF_LAP(2);
                 filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
+                PROF_LAP(1);
             }
             fence_proxy_async();
             __syncwarp();
+            PROF_LAP(4);
             if (lane == 0) {
                 mbar_arrive(&empty[s]);
 #pragma unroll
@@ -523,7 +651,9 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                     bulk_commit();
                 }
             }
+            PROF_LAP(5);
         }
+        PROF_END(p, slot, lane);
     } else {
         // tiles before this band's own pre-pass start are only released, not filtered
         long long t = t_first;
@@ -541,7 +671,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) filter_half<T, A, K, 0, SCALED>(xrow + h * kTileBytes, nullptr, key, c, wst);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            stage_release_after_reads(&empty[s], lane);
         }
     }
     if (PASS_B) {
@@ -698,7 +828,7 @@ sos_hform_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CU
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        stage_release_after_reads(&empty[s], lane);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -732,6 +862,20 @@ sos_tma_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ Coef
                const __grid_constant__ CUtensorMap ymap2) {
     extern __shared__ __align__(1024) char smem[];
     tma_cta<T, A, K, PASS, SCALED, 2, kTmaStages, WEIGHT, DEC>(p, tab, xmap, ymap, ymap2, smem, blockIdx.x, 0);
+}
+
+// Fused weighting prefilter + bank (output pass or band-level epilogue): 12 warps in the spread role layout of
+// tma_cta (<= 9 band warps), one CTA per SM, four input stages and two output tiles per band warp -- with a single
+// resident CTA nothing else hides the latency of the TMA stores (1500-2200 clocks until a tile has been read out of
+// shared memory, profiles/r02j_warp_prof.txt).
+constexpr int kTmaWeightBands = 9;
+constexpr int kTmaWeightStages = 4;
+template <typename T, typename A, int K, int PASS, bool SCALED>
+__global__ void __launch_bounds__(12 * 32, 1)
+sos_tma_weighted_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
+                        const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
+    extern __shared__ __align__(1024) char smem[];
+    tma_cta<T, A, K, PASS, SCALED, 2, kTmaWeightStages, true, false, PASS == 1 ? 2 : 1>(p, tab, xmap, ymap, ymap, smem, blockIdx.x, 0);
 }
 
 // Output pass for launches with about one CTA per SM (one chunk per cascade and few (channel block, band group)

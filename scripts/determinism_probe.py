@@ -13,7 +13,7 @@ def check(name, fn, reps=4):
     print("%-52s equal to run 0: %s  max |diff| %.2e" % (name, same, worst), flush=True)
 
 ofb = p.FractionalOctaveFilterbank(sample_rate=48000)
-for C, n in ((64, 480000), (16, 2880000), (3, 1000001)):
+for C, n in (() if "gammatone" in sys.argv else ((64, 480000), (16, 2880000), (3, 1000001))):
     for dt in (torch.float64, torch.float32):
         x = torch.from_numpy(rng.standard_normal((C, n))).cuda().to(dt)
         for env in ({}, {"PFB_NO_HFORM": "1"}):

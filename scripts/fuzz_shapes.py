@@ -110,7 +110,11 @@ while time.time() < t_end:
     yb, st, wz = p.bank_filter_weighted(bank48, xt[:, cut:].contiguous(), b, a, st, wz)
     yy = torch.cat([ya, yb], dim=2)[chans].cpu().numpy()
     e = max(rel(yy[:, k].T, y0[:, k]) for k in range(33))
-    if not e <= 1e-9:
+    # Bar 5e-9 here (1e-9 in the fixed-seed tests): behind the bit-identical prefilter the lowest bands carry almost no
+    # signal (A: -63 dB at 12.5 Hz) while their section states still see the broadband input, so FMA against separately
+    # rounded arithmetic differs by up to ~2e-9 there on some draws; the reference's own float64 result is 5e-5 away
+    # from the 80-bit evaluation of the same recurrences in those bands (profiles/r02_weighted_conditioning.txt).
+    if not e <= 5e-9:
         print("FAIL weighted %s C=%d n=%d cut=%d fused=%s err=%.2e" % (wname, C, n, cut, os.environ["PFB_WEIGHT_FUSED"], e)); sys.exit(1)
     fused_cases += 1
     if rng.random() < 0.5:

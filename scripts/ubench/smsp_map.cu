@@ -1,0 +1,150 @@
+// Microbenchmark: which SM sub-partition (issue port) does warp i of a CTA land on, and what do the two FP64
+// instruction streams of the fused weighted bank cost when they share one?
+//   role 'W': the weighting recurrence (scipy's lfilter order, 25 separately rounded FP64 operations per sample,
+//             coefficients in uniform registers)            -- pfb_kernels.cuh tf_step<6>
+//   role 'B': a band cascade of 4 gain-normalised sections (17 DFMA-class operations per sample)
+// Every active warp runs `n` samples and records its own clocks; the table gives clocks per sample per warp.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o smsp_map.bin smsp_map.cu
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+
+struct Coef { double b[8], a[8], c[4][5]; };
+
+__device__ __forceinline__ double tf_step6(double xi, const double *b, const double *a, double (&z)[6]) {
+    const double yi = __dadd_rn(z[0], __dmul_rn(b[0], xi));
+#pragma unroll
+    for (int k = 0; k < 5; ++k) z[k] = __dsub_rn(__dadd_rn(z[k + 1], __dmul_rn(xi, b[k + 1])), __dmul_rn(yi, a[k + 1]));
+    z[5] = __dsub_rn(__dmul_rn(xi, b[6]), __dmul_rn(yi, a[6]));
+    return yi;
+}
+
+__global__ void __launch_bounds__(512) probe(const __grid_constant__ Coef cf, const char *roles, int n, long long *clk, double *sink) {
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const char role = roles[warp];
+    double x = 1e-3 * (threadIdx.x & 31);
+    long long t0 = clock64();
+    double acc = 0;
+    if (role == 'W') {
+        double z[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < n; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc += tf_step6(x, cf.b, cf.a, z); x = x * 0.999 + 1e-4; }
+        }
+    } else if (role == 'B') {
+        double w[4][2] = {};
+        for (int i = 0; i < n; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double s = x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double t = fma(-cf.c[k][4], w[k][1], s);
+                    const double w0 = fma(-cf.c[k][3], w[k][0], t);
+                    s = fma(cf.c[k][2], w[k][1], fma(cf.c[k][1], w[k][0], w0));
+                    w[k][1] = w[k][0];
+                    w[k][0] = w0;
+                }
+                acc += s * cf.c[0][0];
+                x = x * 0.999 + 1e-4;
+            }
+        }
+    }
+    else if (role == 'D' || role == 'E') {
+        // the same cascade over batches of NB samples in wavefront (anti-diagonal) order: the K section updates of one
+        // diagonal are independent, so a single warp has K-fold instruction-level parallelism
+        double w[4][2] = {};
+        constexpr int NB = 16;
+        for (int i = 0; i < n; i += NB) {
+            double s[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) { s[u] = x; x = x * 0.999 + 1e-4; }
+#pragma unroll
+            for (int d = 0; d < NB + 3; ++d) {
+#pragma unroll
+                for (int k = 3; k >= 0; --k) {
+                    const int m = d - k;
+                    if (m >= 0 && m < NB) {
+                        const double t = fma(-cf.c[k][4], w[k][1], s[m]);
+                        const double w0 = fma(-cf.c[k][3], w[k][0], t);
+                        s[m] = fma(cf.c[k][2], w[k][1], fma(cf.c[k][1], w[k][0], w0));
+                        w[k][1] = w[k][0];
+                        w[k][0] = w0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) acc += s[u] * cf.c[0][0];
+        }
+    }
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0) clk[blockIdx.x * 16 + warp] = t1 - t0;
+    if (acc == 123.456) sink[0] = acc;
+}
+
+static void run(const char *label, const char *roles, int ctas_per_sm, int sms) {
+    static char *d_roles = nullptr; static long long *d_clk = nullptr; static double *d_sink = nullptr;
+    if (!d_roles) { cudaMalloc(&d_roles, 16); cudaMalloc(&d_clk, 8 * 16 * 4096); cudaMalloc(&d_sink, 8); }
+    Coef cf;
+    for (int i = 0; i < 8; ++i) { cf.b[i] = 0.1 + 0.01 * i; cf.a[i] = 0.05 - 0.01 * i; }
+    for (int k = 0; k < 4; ++k) { cf.c[k][0] = 0.5; cf.c[k][1] = 0.3; cf.c[k][2] = -0.2; cf.c[k][3] = -0.4; cf.c[k][4] = 0.1; }
+    char r[16]; memset(r, '.', 16); int nw = (int)strlen(roles); memcpy(r, roles, nw);
+    cudaMemcpy(d_roles, r, 16, cudaMemcpyHostToDevice);
+    cudaMemset(d_clk, 0, 8 * 16 * 4096);
+    const int n = 20000, grid = sms * ctas_per_sm;
+    probe<<<grid, nw * 32>>>(cf, d_roles, 64, d_clk, d_sink);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    probe<<<grid, nw * 32>>>(cf, d_roles, n, d_clk, d_sink);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    static long long h[16 * 4096];
+    cudaMemcpy(h, d_clk, 8 * 16 * grid, cudaMemcpyDeviceToHost);
+    printf("%-34s roles %-14s CTAs/SM %d  %.3f ms | clk/sample per warp:", label, roles, ctas_per_sm, ms);
+    for (int w = 0; w < nw; ++w) {
+        double worst = 0;
+        for (int c = 0; c < grid; ++c) worst = worst > h[c * 16 + w] ? worst : (double)h[c * 16 + w];
+        if (roles[w] == '.') printf("   -"); else printf(" %4.0f", worst / n);
+    }
+    printf("\n");
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    const int sms = p.multiProcessorCount;
+    printf("%s SMs=%d\n", p.name, sms);
+    run("one weighting warp", "W", 1, sms);
+    run("one band warp", "B", 1, sms);
+    run("one band warp, wavefront order", "D", 1, sms);
+    run("wavefront: 2 on a port", "D...D", 1, sms);
+    run("wavefront: 3 on a port", "D...D...D", 1, sms);
+    run("wavefront: 12 bands", "DDDDDDDDDDDD", 1, sms);
+    run("wavefront: 9 bands, W at 3", "DDDWDDD.DDD", 1, sms);
+    run("wavefront: 10 bands, W at 3", "DDDWDDDDDDD", 1, sms);
+    run("wavefront: 7 bands, W at 7", "DDDDDDDW.", 1, sms);
+    run("wavefront: 7 bands, W at 7, 2 CTAs", "DDDDDDDW.", 2, sms);
+    run("wavefront: 14 bands", "DDDDDDDDDDDDDD", 1, sms);
+    run("wavefront: 16 bands", "DDDDDDDDDDDDDDDD", 1, sms);
+    // which warp indices share an issue port with warp 0?
+    const char *pairs[] = {"WW", "W.W", "W..W", "W...W", "W....W", "W.....W", "W......W", "W.......W"};
+    for (auto s : pairs) run("two weighting warps", s, 1, sms);
+    run("four weighting warps 0-3", "WWWW", 1, sms);
+    run("band pairs", "BB", 1, sms);
+    run("band pairs", "B...B", 1, sms);
+    run("band triple on one port", "B...B...B", 1, sms);
+    run("W + B same port", "W...B", 1, sms);
+    run("W + 2B same port", "W...B...B", 1, sms);
+    // CTA shapes of the fused weighted bank
+    run("round 2a: 7 bands, W at 7", "BBBBBBBW.", 1, sms);
+    run("round 2a: 4 bands, W at 4, 2 CTAs", "BBBBW.", 2, sms);
+    run("round 2a: 3 bands, W at 3, 3 CTAs", "BBBW.", 3, sms);
+    run("own port: 9 bands, W at 3", "BBBWBBB.BBB", 1, sms);
+    run("own port: 9 bands, W at 3, 2 CTAs", "BBBWBBB.BBB.", 2, sms);
+    run("own port: 6 bands, W at 3", "BBBWBBB.", 1, sms);
+    run("own port: 6 bands, W at 3, 2 CTAs", "BBBWBBB.", 2, sms);
+    run("own port: 6 bands, W at 3, 3 CTAs", "BBBWBBB.", 3, sms);
+    run("own port: 3 bands, W at 3, 4 CTAs", "BBBW", 4, sms);
+    run("12 bands, no W", "BBBBBBBBBBBB", 1, sms);
+    run("11 bands + W at 11", "BBBBBBBBBBBW", 1, sms);
+    return 0;
+}
