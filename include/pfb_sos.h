@@ -227,6 +227,27 @@ PFB_API int pfb_bank_release_stream(pfb_bank *bank, void *stream);
 /* device allocations made by this library so far (diagnostics / tests) */
 PFB_API long long pfb_device_allocs(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * On-device coefficient design and the 'py' state adapter
+ * ------------------------------------------------------------------------------------------------
+ * pfb_design_butter_sos replaces, for B bands at once, butter_sos(band, L, v1, v2)
+ * (pyfilterbank/butterworth.py:16-58 with butter_analog_sos :61-146 and bilinear_sos,
+ * pyfilterbank/sosfiltering.py:382-432): kind 0 low-pass, 1 high-pass, 2 band-pass, 3 band-stop; L low-pass poles
+ * (even); v1[B] (and v2[B] for kinds 2, 3) HOST arrays of critical frequencies in cycles per sample, 0 < v1 < v2 < 0.5
+ * (PFB_ERR_INVALID otherwise, like the reference's exceptions).  Result: [B][K][6] rows [b0 b1 b2 a0 a1 a2], a0 == 1,
+ * sections in the reference's (reversed) order, K = L for kinds 2, 3 and L / 2 otherwise -- column b of
+ * FractionalOctaveFilterbank.sosmat is row b flattened (octbank.py:165-172).  Written to sos_host (HOST, may be null)
+ * and / or sos_dev (DEVICE, may be null).  Synchronises the stream. */
+PFB_API int pfb_design_butter_sos(int kind, int L, const double *v1, const double *v2, int B, double *sos_host,
+                                  double *sos_dev, void *stream);
+/* States of the reference's 'py' filter function (sosfilter_py, sosfiltering.py:368-379: scipy.signal.lfilter per
+ * section, zi = Direct-Form-II-Transposed delay values) <-> the (w1, w2) Direct-Form-II delay values of sosfilt.c and of
+ * every kernel here.  states_dev DEVICE [Q][K][2], converted in place; sos HOST [B][K][6] (row q uses bank row q % B)
+ * or, per_row != 0, [Q][K][6]; to_df2t != 0: (w1, w2) -> (z1, z2), else the inverse (PFB_ERR_INVALID when a section's
+ * numerator and denominator share a root).  a0 normalises the section as scipy does.  Synchronises the stream. */
+PFB_API int pfb_states_convert(double *states_dev, const double *sos, int64_t Q, int B, int K, int per_row, int to_df2t,
+                               void *stream);
+
 PFB_API const char *pfb_version(void);
 
 #ifdef __cplusplus

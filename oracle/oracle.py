@@ -193,6 +193,20 @@ def lfilter_df2t(b, a, x, zi=None):
     return y, z
 
 
+def sosfilter_py(x, sos, states=None):
+    """The reference's `sosfilter_py` (sosfiltering.py:330-379): `lfilter(b, a, x, 0, zi)` section by section, states a
+    dict {section index: zi (2,)} of Direct-Form-II-Transposed delay values.  x 1-D float64."""
+    sos = np.asarray(sos, np.float64).reshape(-1, 6)
+    n = sos.shape[0]
+    if states is None:
+        states = {i: np.zeros(2) for i in range(n)}
+    x = np.asarray(x, np.float64)
+    for i in range(n):
+        x, zi = lfilter_df2t(sos[i, :3], sos[i, 3:], x, states[i])
+        states[i] = zi
+    return x, states
+
+
 # ---------------------------------------------------------------------------------------------
 # Composed paths (no single reference function exists; composed from the pieces above exactly like
 # tests/golden/make_golden_composed.py composes the reference's own functions).

@@ -71,6 +71,10 @@ def lib():
         L.pfb_bank_release_stream.argtypes = [vp, vp]
         L.pfb_bank_release_stream.restype = ci
         L.pfb_device_allocs.restype = ctypes.c_longlong
+        L.pfb_design_butter_sos.argtypes = [ci, ci, vp, vp, ci, vp, vp, vp]
+        L.pfb_design_butter_sos.restype = ci
+        L.pfb_states_convert.argtypes = [vp, vp, i64, ci, ci, ci, ci, vp]
+        L.pfb_states_convert.restype = ci
         L.pfb_decbank_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(ci), ctypes.POINTER(vp), ci, vp, ci]
         L.pfb_decbank_create.restype = ci
         L.pfb_decbank_destroy.argtypes = [vp]

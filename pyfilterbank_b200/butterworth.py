@@ -64,6 +64,33 @@ def butter_analog_sos(band, L, w1, w2=0):
     raise Exception("band must be one of 'lowpass', 'highpass', 'bandpass', 'bandstop'")
 
 
+_KINDS = {lowpass: 0, highpass: 1, bandpass: 2, bandstop: 3}
+
+
+def butter_sos_cuda(band, L, v1, v2=None, device_out=False):
+    """`butter_sos` for B bands at once on the GPU (pfb_design_butter_sos, csrc/pfb_design.cu): v1, v2 arrays of
+    critical frequencies in cycles per sample.  Returns (B, K, 6) rows in the reference's order (K = L for band-pass /
+    band-stop, L / 2 otherwise) as a numpy array, or with device_out=True additionally as a CUDA tensor.  Raises
+    PfbError for frequencies outside 0 < v1 < v2 < 0.5, like the reference's exceptions (butterworth.py:44-47)."""
+    import torch
+    from . import _lib
+    kind = _KINDS[band.lower()]
+    if L % 2:
+        raise Exception('Number of poles L must be even')
+    v1 = np.ascontiguousarray(np.atleast_1d(v1), dtype=np.float64)
+    B = len(v1)
+    v2a = None if kind < 2 else np.ascontiguousarray(np.atleast_1d(v2), dtype=np.float64)
+    if v2a is not None and len(v2a) != B:
+        raise ValueError("v1 and v2 must have the same length")
+    K = L if kind >= 2 else L // 2
+    out = np.empty((B, K, 6))
+    dev_t = torch.empty((B, K, 6), dtype=torch.float64, device="cuda") if device_out else None
+    _lib.check(_lib.lib().pfb_design_butter_sos(kind, L, v1.ctypes.data, None if v2a is None else v2a.ctypes.data, B,
+                                                out.ctypes.data, None if dev_t is None else dev_t.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream))
+    return (out, dev_t) if device_out else out
+
+
 def butter_sos(band, L, v1, v2=0.0):
     """Digital Butterworth cascade: rows [b0 b1 b2 a0 a1 a2] (a0 == 1), one per section; L/2
     sections for low/high-pass, L for band-pass/-stop.  v1, v2 are critical frequencies in

@@ -62,14 +62,21 @@ def to_normalized_frequencies(frequencies, sample_rate, clip=True):
     return frequencies[~over] / sample_rate
 
 
-def design_sosmat_band_passes(order, band_edges, sample_rate, edge_correction_percent=0.0):
+def design_sosmat_band_passes(order, band_edges, sample_rate, edge_correction_percent=0.0, device=False):
     """(order*6, num_bands) matrix; column b holds band b's `order` biquads
-    [b0 b1 b2 a0 a1 a2] flattened row-major.  octbank.py:132-173."""
+    [b0 b1 b2 a0 a1 a2] flattened row-major.  octbank.py:132-173.
+    device=True designs all bands in one CUDA kernel (butterworth.butter_sos_cuda) instead of the numpy loop."""
     num_bands = len(band_edges) - 1
     sosmat = np.zeros((order * 6, num_bands))
     edges = to_normalized_frequencies(band_edges, sample_rate)
     lo_scale = 1 - edge_correction_percent * 1e-2
     hi_scale = 1 + edge_correction_percent * 1e-2
+    if device:
+        from .butterworth import butter_sos_cuda
+        nb = len(edges) - 1
+        if nb > 0:
+            sosmat[:, :nb] = butter_sos_cuda('bandpass', order, lo_scale * edges[:-1], hi_scale * edges[1:]).reshape(nb, -1).T
+        return sosmat
     for i in range(len(edges) - 1):
         sosmat[:, i] = butter_sos('bandpass', order, lo_scale * edges[i], hi_scale * edges[i + 1]).flatten()
     return sosmat
@@ -80,7 +87,10 @@ class FractionalOctaveFilterbank:
     arguments, properties and `filter` / `filter_mimo_c` signatures and return conventions."""
 
     def __init__(self, sample_rate=44100, order=4, nth_oct=3.0, norm_freq=1000.0, start_band=-19,
-                 end_band=13, edge_correction_percent=0.01, filterfun='cuda'):
+                 end_band=13, edge_correction_percent=0.01, filterfun='cuda', design='host'):
+        if design not in ('host', 'device'):
+            raise ValueError("design must be 'host' (numpy) or 'device' (CUDA kernel)")
+        self._design = design
         self._sample_rate = sample_rate
         self._order = order
         self._nth_oct = nth_oct
@@ -123,7 +133,7 @@ class FractionalOctaveFilterbank:
         self._center_frequencies, self._band_edges = frequencies_fractional_octaves(
             self.start_band, self.end_band, self.norm_freq, self.nth_oct)
         self._sosmat = design_sosmat_band_passes(self.order, self.band_edges, self.sample_rate,
-                                                 self.edge_correction_percent)
+                                                 self.edge_correction_percent, device=self._design == 'device')
         self._dec_plan = None
 
     # ------------------------------------------------------------------------------------------
@@ -259,16 +269,26 @@ class FractionalOctaveFilterbank:
 
     def set_filterfun(self, filterfun_name):
         name = filterfun_name.lower()
+        self._py_states = False
         if name in ('cuda', 'cffi'):
             self._exact = False
         elif name == 'exact':
             self._exact = True
+        elif name == 'py':
+            # the STATE CONVENTION of the reference's 'py' filter function (sosfilter_py: dict {section: lfilter zi}
+            # per band, octbank.py:402-404), computed by the CUDA kernels; not a CPU path
+            self._exact = False
+            self._py_states = True
         else:
-            raise ValueError("filterfun must be 'cuda' (alias 'cffi') or 'exact'; this package has no CPU path")
+            raise ValueError("filterfun must be 'cuda' (alias 'cffi'), 'exact' or 'py' (state convention of the "
+                             "reference's lfilter path); this package has no CPU path")
         self.filterfun_name = name
         mode = "seq" if self._exact else "auto"
-        self.sosfilterfun = lambda x, sos, states=None: _sf.sosfilter_double_c(
-            x, sos, states, mode=mode, exact=self._exact)
+        if self._py_states:
+            self.sosfilterfun = _sf.sosfilter_py
+        else:
+            self.sosfilterfun = lambda x, sos, states=None: _sf.sosfilter_double_c(
+                x, sos, states, mode=mode, exact=self._exact)
 
     def filter_mimo_c(self, x, states=None, weighting=None, weighting_states=None):
         """(N,) or (N, C) signal -> ((N, B, C) Fortran-ordered bands, flat states); octbank.py:412-434.
@@ -343,12 +363,18 @@ class FractionalOctaveFilterbank:
         B, K = self.num_bands, self.order
         cfs = self.center_frequencies
         st = None
+        py = getattr(self, '_py_states', False)
+        sos_rows = np.ascontiguousarray(self.sosmat.T).reshape(B, K, 6)
         if isinstance(states, dict):
             rows = []
             for f in cfs:
                 s = states[f]
                 if s is None:
                     rows.append(np.zeros(2 * K))
+                elif py:                                  # {section index: zi (2,)}, sosfiltering.py:368-379
+                    rows.append(np.concatenate([np.asarray(
+                        s[i].detach().cpu().numpy() if isinstance(s[i], torch.Tensor) else s[i], dtype=np.float64).reshape(2)
+                        for i in range(K)]))
                 elif isinstance(s, torch.Tensor):
                     rows.append(s.detach().cpu().numpy().reshape(-1))
                 else:
@@ -362,6 +388,8 @@ class FractionalOctaveFilterbank:
             dev = _sf._device()
             sig = torch.from_numpy(np.array(x, dtype=np.float64).flatten()[:n]).to(dev)
         st_t = None if st is None else torch.from_numpy(st).to(dev)
+        if py and st_t is not None:
+            _sf.states_convert(st_t, sos_rows, to_df2t=False)          # lfilter zi -> (w1, w2), on the device
         mode = "seq" if self._exact else "auto"
         if not ffilt:
             y, st_t = _sf.bank_filter(bank, sig.reshape(1, n), st_t, mode=mode, exact=self._exact)
@@ -373,6 +401,11 @@ class FractionalOctaveFilterbank:
             bank2 = _sf.get_bank(np.ascontiguousarray(self.sosmat.T).reshape(B, 1, K, 6))
             y2, st_t = _sf.bank_filter(bank2, rows, st_t.reshape(B, 1, K, 2), mode=mode, exact=self._exact)
             y = y2[:, 0]
+        if py:
+            st_t = _sf.states_convert(st_t.reshape(1, B, K, 2).contiguous(), sos_rows, to_df2t=True)
+            st_np = st_t.reshape(B, K, 2).cpu().numpy()
+            st_py = {f: {k: st_np[i, k].copy() for k in range(K)} for i, f in enumerate(cfs)}
+            return (y.t(), st_py) if on_device else (_sf._to_host(y.t().contiguous()), st_py)
         st_rows = st_t.reshape(B, 2 * K)
         if on_device:
             return y.t(), {f: st_rows[i] for i, f in enumerate(cfs)}

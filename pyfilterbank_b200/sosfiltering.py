@@ -17,8 +17,8 @@ import torch
 from . import _lib
 from ._lib import Bank
 
-__all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "bank_filter", "bank_levels",
-           "bank_filter_weighted", "bilinear_sos", "get_bank"]
+__all__ = ["sosfilter_c", "sosfilter_double_c", "sosfilter_double_mimo_c", "sosfilter_py", "bank_filter", "bank_levels",
+           "bank_filter_weighted", "bilinear_sos", "get_bank", "states_convert"]
 
 _bank_cache = collections.OrderedDict()
 
@@ -228,6 +228,64 @@ def sosfilter_c(signal, sos, states=None, *, mode="auto", exact=False, arith64=F
 def sosfilter_double_c(signal, sos, states=None, *, mode="auto", exact=False):
     """float64 cascade, the reference's `sosfilter_double_c` (sosfiltering.py:111-163)."""
     return _single(signal, sos, states, np.float64, torch.float64, mode, exact, False)
+
+
+def states_convert(states, sos, to_df2t):
+    """Convert filter memory in place between the two conventions the reference uses: the (w1, w2) Direct-Form-II
+    delay values of sosfilt.c (and of every kernel here) and the Direct-Form-II-Transposed `zi` of scipy.signal.lfilter
+    that the reference's `sosfilter_py` carries (sosfiltering.py:368-379).  states: float64 CUDA tensor (..., K, 2),
+    contiguous; sos (B, K, 6) shared by rows (row q uses bank row q % B) or one row set per cascade (Q, K, 6).
+    Runs as a CUDA kernel (pfb_states_convert).  Returns `states`."""
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    K = sos.shape[-2]
+    if not (states.is_cuda and states.dtype == torch.float64 and states.is_contiguous() and states.shape[-2:] == (K, 2)):
+        raise ValueError("states must be a contiguous float64 CUDA tensor (..., %d, 2)" % K)
+    Q = states.numel() // (2 * K)
+    rows = sos.reshape(-1, K, 6)
+    per_row = int(rows.shape[0] == Q and Q > 1 and sos.ndim > 3)
+    if not per_row and Q % rows.shape[0]:
+        raise ValueError("%d cascades do not divide into banks of %d rows" % (Q, rows.shape[0]))
+    _lib.check(_lib.lib().pfb_states_convert(states.data_ptr(), rows.ctypes.data, Q, rows.shape[0], K, per_row, int(bool(to_df2t)),
+                                             torch.cuda.current_stream().cuda_stream))
+    return states
+
+
+def sosfilter_py(x, sos, states=None):
+    """The reference's `sosfilter_py` (sosfiltering.py:330-379) on the GPU: sos (K, 6) rows [b0 b1 b2 a0 a1 a2] (a0
+    normalises the section, like scipy.signal.lfilter), `states` None or a dict {section index: zi (2,)} of
+    Direct-Form-II-Transposed delay values -- what lfilter returns and what the reference's 'py' filter function carries
+    between blocks.  Returns (y (N,), states dict).  The cascade runs in the bank kernels (Direct Form II); the state
+    adapter kernel (pfb_states_convert) maps the carried values between the two forms on the device, so blocks filtered
+    here continue blocks filtered by the reference's sosfilter_py and vice versa (to ~1e-10: the two forms round
+    differently)."""
+    on_device = isinstance(x, torch.Tensor) and x.is_cuda
+    dev = x.device if on_device else _device()
+    rows = _sos_rows(sos.detach().cpu().numpy() if isinstance(sos, torch.Tensor) else sos)
+    K = rows.shape[0]
+    rows = rows / rows[:, 3:4]                                # lfilter divides by a0; sosfilt.c would ignore it
+    zi = np.zeros((K, 2))
+    if states is not None:
+        for i in range(K):
+            zi[i] = np.asarray(states[i].detach().cpu().numpy() if isinstance(states[i], torch.Tensor) else states[i],
+                               dtype=np.float64).reshape(2)
+    st = torch.from_numpy(zi.reshape(1, 1, K, 2)).to(dev)
+    states_convert(st, rows.reshape(1, K, 6), to_df2t=False)
+    n = len(x)
+    if on_device:
+        sig = x.detach().to(torch.float64).reshape(1, n)
+    else:
+        sig = torch.from_numpy(np.array(x, dtype=np.float64).reshape(1, n)).to(dev)
+    bank = get_bank(rows.reshape(1, K, 6))
+    y, st = bank_filter(bank, sig.contiguous(), st)
+    states_convert(st, rows.reshape(1, K, 6), to_df2t=True)
+    y = y.reshape(n)
+    out = states if states is not None else dict()       # like the reference, a dict passed in is updated and returned
+    if on_device:
+        out.update({i: st[0, 0, i] for i in range(K)})
+        return y, out
+    st = st.cpu().numpy()
+    out.update({i: st[0, 0, i].copy() for i in range(K)})
+    return y.cpu().numpy(), out
 
 
 def sosfilter_double_mimo_c(signal, sos, states=None, *, mode="auto", exact=False):
