@@ -252,6 +252,9 @@ __device__ __forceinline__ A section_step(A x, const A *c, A &w1, A &w2) {
 #ifndef PFB_W_ROLLED
 #define PFB_W_ROLLED 0
 #endif
+#ifndef PFB_ONE_COMMIT
+#define PFB_ONE_COMMIT 0     // output pass: one bulk group per tile instead of one per 128-byte half row
+#endif
 template <typename T, typename A, int K, bool SCALED, int NS, typename Out>
 __device__ __forceinline__ void cascade_wave(const T *e, const A (&c)[K][5], A (&w)[K][2], Out out) {
 #if PFB_WAVE
@@ -634,8 +637,15 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
                 // (YB buffers: the groups of the YB - 1 tiles in between may still be pending)
+#if PFB_ONE_COMMIT
+                if (h == 0) {     // one bulk group per tile: the whole previous tile must have been read
+                    if (lane == 0) bulk_wait_read_upto(YB - 1);
+                    __syncwarp();
+                }
+#else
                 if (lane == 0) bulk_wait_read_upto((YB - 1) * NH + NH - 1 - h);
                 __syncwarp();
+#endif
                 PROF_LAP(2);
                 filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
                 PROF_LAP(1);
@@ -648,8 +658,13 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
                     tma_store_4d(&ymap, ybuf + yb + h * kTileBytes, (int)(t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
+#if !PFB_ONE_COMMIT
                     bulk_commit();
+#endif
                 }
+#if PFB_ONE_COMMIT
+                bulk_commit();
+#endif
             }
             PROF_LAP(5);
         }

@@ -55,7 +55,7 @@ def test_octbank_exact_mode_bitwise(pfb):
     assert np.array_equal(y, g["y_ffilt_ch0"])
     assert np.array_equal(np.stack([states[f] for f in ofb.center_frequencies]), g["states_ffilt_ch0"])
     with pytest.raises(ValueError):
-        pfb.FractionalOctaveFilterbank(filterfun='py')      # no CPU path in this package
+        pfb.FractionalOctaveFilterbank(filterfun='cprototype')      # no CPU path in this package ('py' = state convention only)
 
 
 def test_gammatone_golden(pfb):
