@@ -555,10 +555,12 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
 // One (pre-pass, carry, output | levels) launch set over J chunks of Lt samples.  Caller holds b->mu.
 static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long long ldx, void *y, long long ldy, void *states,
                    long long Lt, int J, int C, int nb, int G, cudaStream_t stream, double *levels, long long lev_ld,
-                   long long lev_off, int ut, bool may_time, bool wide = false, const FilterExtra *ex = nullptr) {
+                   long long lev_off, int ut, bool may_time, bool wide = false, const FilterExtra *ex = nullptr, int jr_req = 0) {
     const int arith = arith64 ? PFB_F64 : PFB_F32;
     const int tt = 2 * pfb::kRowBytes / (dtype == PFB_F64 ? 8 : 4);
-    const int JR = std::min(J, 32), CH = 32 / JR;
+    // rows of a tile: JR chunks x CH channels; default JR = min(J, 32), a smaller JR (J = JR * chunk groups) spreads a
+    // tile over more channels -- the chunked regime then has CTA counts other than multiples of 32 * groups
+    const int JR = jr_req > 0 ? jr_req : std::min(J, 32), CH = 32 / JR;
     const int Q = C * b->B;
     const Tables *tab = nullptr;
     if (J > 1) {
@@ -942,6 +944,7 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
             }
         }
         const int ttb = wide ? 2 * tt : tt;
+        int jr_plan = 0;
         if (wide) {
             tma_bands(b, &nb, &G, true);
             // Few chunks mean little pre-pass work; the wide kernel runs one CTA per SM, so the grid is sized in
@@ -956,12 +959,16 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
                 J = tma_pick_J(b, n, C, ttb, arith64, G, 1 << 30, true);
             }
         }
-        const int JR = std::min(J, 32);
+        int JR = std::min(J, 32);
+        if (jr_plan > 0 && J % jr_plan == 0) JR = jr_plan;
+        if (const int jr_env = env_int("PFB_TMA_JR", 0)) {
+            if (jr_env > 0 && jr_env <= 32 && 32 % jr_env == 0 && J % jr_env == 0) JR = jr_env;
+        }
         if (J <= 0 || J % JR != 0 || 32 % JR != 0) return fail(PFB_ERR_INVALID, "pfb_bank_filter: bad chunk count %d", J);
         const long long Lt = n / J / ttb * ttb;
         if (Lt >= 4LL * ttb && Lt < 0x7fffffffLL) {
             const long long n_main = Lt * J;
-            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true, wide, ex);
+            rc = tma_run(b, dtype, arith64, x, ldx, y, ldy, states, Lt, J, C, nb, G, stream, nullptr, 0, 0, 0, true, wide, ex, JR);
             if (rc) return rc;
             if (ex) {                // fused stages: the caller finishes the ragged end
                 ex->n_done = n_main;
