@@ -311,6 +311,21 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
                    {"workload": "A-weighting + 1/3-octave bank, %d of 8192 channels per GPU, %d blocks of 0.5 s @ 48 kHz "
                                 "with carried states, %s" % (C, blocks, "float32" if esz == 4 else "float64"),
                     "path": bank.last_launch()["aligned"]})
+            if esz == 4:   # the monitoring form of cfg 5: A-weighted band energies per 0.1 s, no band signal written
+                st.zero_()
+                wz.zero_()
+                del y
+
+                def run_lev():
+                    for _ in range(blocks):
+                        pfb.bank_levels(bank, x, 4800, st, weighting=(b, a), wz=wz)
+                ms = event_time(torch, run_lev, 2, 1)
+                finish("cfg5_f32_levels", ms, C * B * nblk * blocks, C * nblk * blocks * esz,
+                       {"workload": "A-weighting + 1/3-octave bank + band energies per 0.1 s in one kernel "
+                                    "(pfb_bank_levels_weighted), %d of 8192 channels per GPU, %d blocks of 0.5 s, float32: "
+                                    "only the input is read (roofline_frac counts those bytes; the kernel is FP32/FP64-issue "
+                                    "bound)" % (C, blocks)})
+                y = None
             del x, y, st, wz
             torch.cuda.empty_cache()
     except Exception as e:

@@ -99,6 +99,13 @@ PFB_API int pfb_bank_filter(pfb_bank *bank, int dtype, const void *x, int64_t ld
  * States are carried like in pfb_bank_filter. */
 PFB_API int pfb_bank_levels(pfb_bank *bank, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
                             void *states, int64_t n, int C, int64_t block_len, int flags, void *stream);
+/* The same with the SPL-weighting prefilter in front (splweighting.py:61-80 `weight_signal`, then `filter_mimo_c`, then
+ * 10 log10 sum y^2 -- octbank.py:262-263): prefilter, bank and energies in ONE kernel, only the input is read from HBM.
+ * wb / wa: transfer-function taps like pfb_bank_filter_weighted (5 to 7 taps), wz DEVICE [C][ntaps-1] delay values
+ * (scipy's zi) in/out. */
+PFB_API int pfb_bank_levels_weighted(pfb_bank *bank, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
+                                     void *states, const double *wb, int nwb, const double *wa, int nwa, double *wz,
+                                     int64_t n, int C, int64_t block_len, int flags, void *stream);
 
 /* pfb_bank_levels on HOST buffers: the input streams through the device in channel groups, only the energies come back
  * (levels [C*B][ld_levels] on the host).  Synchronous. */

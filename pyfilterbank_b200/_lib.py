@@ -48,6 +48,8 @@ def lib():
         L.pfb_bank_filter.restype = ci
         L.pfb_bank_levels.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, i64, ci, vp]
         L.pfb_bank_levels.restype = ci
+        L.pfb_bank_levels_weighted.argtypes = [vp, ci, vp, i64, vp, i64, vp, vp, ci, vp, ci, vp, i64, ci, i64, ci, vp]
+        L.pfb_bank_levels_weighted.restype = ci
         L.pfb_bank_levels_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, i64, ci]
         L.pfb_bank_levels_host.restype = ci
         L.pfb_bank_filter_host.argtypes = [vp, ci, vp, i64, vp, i64, vp, i64, ci, ci]
@@ -165,6 +167,12 @@ class Bank:
 
     def levels_ptr(self, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags=0, stream=0):
         check(lib().pfb_bank_levels(self._h, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, n, C, block_len, flags, stream))
+
+    def levels_weighted_ptr(self, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, b, a, wz_ptr, n, C, block_len, flags=0, stream=0):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        check(lib().pfb_bank_levels_weighted(self._h, dtype, x_ptr, ldx, lev_ptr, ld_lev, states_ptr, b.ctypes.data, len(b),
+                                             a.ctypes.data, len(a), wz_ptr, n, C, block_len, flags, stream))
 
     def levels_host(self, dtype, x, ldx, levels, ld_lev, states, n, C, block_len, flags=0):
         check(lib().pfb_bank_levels_host(self._h, dtype, x.ctypes.data, ldx, levels.ctypes.data, ld_lev,

@@ -1225,8 +1225,8 @@ static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_
 #undef PFB_CUDA_C
 }
 
-int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels, void *states,
-                    int64_t n, int C, int64_t block_len, int flags, void *stream_) {
+static int levels_impl(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels, void *states,
+                       int64_t n, int C, int64_t block_len, int flags, void *stream_, FilterExtra *ex) {
     if (!b || !x || !levels || !states) return fail(PFB_ERR_INVALID, "pfb_bank_levels: null argument");
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_levels: bad dtype %d", dtype);
     const int esz = dtype == PFB_F64 ? 8 : 4;
@@ -1261,19 +1261,23 @@ int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *
     }
     int nb, G;
     tma_bands(b, &nb, &G);
+    if (ex && ex->wnz) {   // fused weighting prefilter: rows are whole channels, <= 9 bands per CTA (sos_tma_weighted_kernel)
+        G = (b->B + pfb::kTmaWeightBands - 1) / pfb::kTmaWeightBands;
+        nb = (b->B + G - 1) / G;
+    }
     const long long min_units = (4LL * tt + unit - 1) / unit;   // a chunk is at least four tile steps
     long long pos = 0;
     int kernels = 0;
     while (pos < nunits) {
         const long long rem = nunits - pos;
-        int J = tma_pick_J(b, rem * unit, C, tt, arith64, G, std::max<long long>(1, rem / min_units));
+        int J = ex && ex->wnz ? 1 : tma_pick_J(b, rem * unit, C, tt, arith64, G, std::max<long long>(1, rem / min_units));
         if (J > rem) J = 1;
         const int JR = std::min(J, 32);
         if (J % JR != 0 || 32 % JR != 0) J = 1;
         const long long Lu = rem / J;
         if (Lu * unit >= 0x7fffffffLL) return fail(PFB_ERR_INVALID, "pfb_bank_levels: signal too long for one call");
         int rc = tma_run(b, dtype, arith64, (const char *)x + pos * unit * esz, ldx, nullptr, 0, states, Lu * unit, J, C, nb, G,
-                         stream, partial, pld, pos, (int)(unit / tt), pos == 0);
+                         stream, partial, pld, pos, (int)(unit / tt), pos == 0, false, ex);
         if (rc) return rc;
         kernels += b->last.kernels;
         pos += (long long)J * Lu;
@@ -1289,6 +1293,32 @@ int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *
     b->last.kernels = kernels;
     g_status = PFB_OK;
     return PFB_OK;
+}
+
+int pfb_bank_levels(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels, void *states,
+                    int64_t n, int C, int64_t block_len, int flags, void *stream_) {
+    return levels_impl(b, dtype, x, ldx, levels, ld_levels, states, n, C, block_len, flags, stream_, nullptr);
+}
+
+// Weighted band levels: SPL-weighting prefilter (splweighting.py:61-80) + bank + energies per block in ONE kernel -- the
+// sound-level-meter use of the reference's pieces (weight_signal, filter_mimo_c, 10 log10 sum y^2: octbank.py:262-263):
+// neither the weighted signal nor a band signal is written, only the input is read.
+int pfb_bank_levels_weighted(pfb_bank *b, int dtype, const void *x, int64_t ldx, double *levels, int64_t ld_levels,
+                             void *states, const double *wb, int nwb, const double *wa, int nwa, double *wz, int64_t n, int C,
+                             int64_t block_len, int flags, void *stream_) {
+    if (!b || !wb || !wa || !wz || nwb < 1 || nwa < 1 || nwb > 8 || nwa > 8)
+        return fail(PFB_ERR_INVALID, "pfb_bank_levels_weighted: bad argument (at most 8 taps)");
+    if (wa[0] == 0.0) return fail(PFB_ERR_INVALID, "pfb_bank_levels_weighted: a[0] must not be 0");
+    const int nz = std::max(std::max(nwb, nwa) - 1, 1);
+    if (nz < 4 || nz > 6) return fail(PFB_ERR_INVALID, "pfb_bank_levels_weighted: the fused prefilter takes 5 to 7 taps");
+    FilterExtra ex;
+    for (int k = 0; k < 8; ++k) {   // scipy normalises by a[0] first
+        ex.wb[k] = k < nwb ? wb[k] / wa[0] : 0.0;
+        ex.wa[k] = k < nwa ? wa[k] / wa[0] : 0.0;
+    }
+    ex.wnz = nz;
+    ex.wz = wz;
+    return levels_impl(b, dtype, x, ldx, levels, ld_levels, states, n, C, block_len, flags, stream_, &ex);
 }
 
 int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy, void *states,

@@ -325,12 +325,15 @@ class FractionalOctaveFilterbank:
             return y, st, wst
         return _sf._to_host(yb).transpose(2, 1, 0), st.cpu().numpy(), wst.cpu().numpy()
 
-    def filter_levels(self, x, block_len=None, states=None, db=False):
+    def filter_levels(self, x, block_len=None, states=None, db=False, weighting=None, weighting_states=None):
         """Band energies without the band signals (opt-in; the reference's users compute
         `10*log10(sum(y**2))` from filter_mimo_c's output, octbank.py:262-263): x (N,) or (N, C) ->
         (energy (N // block_len, B, C), flat states like filter_mimo_c).  The squares are summed inside
         the filtering kernel, so nothing of size N*B*C is written.  N must be a multiple of block_len
-        (None: the whole signal) and block_len of 32 samples.  db=True returns 10*log10(energy)."""
+        (None: the whole signal) and block_len of 32 samples.  db=True returns 10*log10(energy).
+        weighting='A' | 'B' | 'C': the SPL weighting prefilter of splweighting.weight_signal (splweighting.py:61-80) runs
+        inside the same kernel in front of the bank -- A-weighted band levels with nothing but the input read from
+        memory; the call then returns (energy, states, weighting_states) like filter_mimo_c(weighting=...)."""
         on_device = isinstance(x, torch.Tensor) and x.is_cuda
         if on_device:
             sig = x.detach().to(torch.float64)
@@ -344,11 +347,23 @@ class FractionalOctaveFilterbank:
         if states is not None:
             st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.array(states, dtype=np.float64))
             st = st.to(device=rows.device, dtype=torch.float64).reshape(C, B, K, 2).clone()
-        e, st = _sf.bank_levels(bank, rows, block_len, st)
+        wst = None
+        if weighting is not None:
+            from . import splweighting as _spl
+            wb, wa = _spl._weighting_coeff_design_funsd[weighting](self.sample_rate)
+            if weighting_states is not None:
+                wst = weighting_states if isinstance(weighting_states, torch.Tensor) else torch.from_numpy(
+                    np.array(weighting_states, dtype=np.float64))
+                wst = wst.to(device=rows.device, dtype=torch.float64).contiguous().clone()
+            e, st, wst = _sf.bank_levels(bank, rows, block_len, st, weighting=(wb, wa), wz=wst)
+        else:
+            e, st = _sf.bank_levels(bank, rows, block_len, st)
         e = e.permute(2, 1, 0)
         if db:
             e = 10.0 * torch.log10(e)
         st = st.reshape(-1)
+        if weighting is not None:
+            return (e, st, wst) if on_device else (e.cpu().numpy(), st.cpu().numpy(), wst.cpu().numpy())
         if on_device:
             return e, st
         return e.cpu().numpy(), st.cpu().numpy()

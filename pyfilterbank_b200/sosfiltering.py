@@ -132,10 +132,13 @@ def bank_filter(bank, x, states=None, *, mode="auto", exact=False, arith64=False
     return out, states
 
 
-def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
+def bank_levels(bank, x, block_len=None, states=None, *, arith64=False, weighting=None, wz=None):
     """Band energies of x (C, N) CUDA tensor through `bank` without materialising the band signals:
     returns (energy (C, B, N // block_len) float64 = sum of y^2 per block, states).  block_len=None: one
-    block = the whole signal.  N must be a multiple of block_len, block_len of 32 (float64) / 64 (float32)."""
+    block = the whole signal.  N must be a multiple of block_len, block_len of 32 (float64) / 64 (float32).
+    weighting=(b, a): transfer-function taps of an SPL-weighting prefilter (5 to 7 taps) run inside the same kernel in
+    front of the bank (pfb_bank_levels_weighted); wz (C, ntaps - 1) float64 delay values (scipy's zi, None: zeros);
+    the call then returns (energy, states, wz)."""
     if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
         raise ValueError("x must be a (C, N) CUDA tensor with contiguous rows")
     C, N = x.shape
@@ -151,6 +154,17 @@ def bank_levels(bank, x, block_len=None, states=None, *, arith64=False):
     nblocks = N // block_len if block_len > 0 else 0
     out = torch.empty((C, B, max(nblocks, 1)), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
+        if weighting is not None:
+            wb, wa = (np.ascontiguousarray(t, dtype=np.float64) for t in weighting)
+            nz = max(len(wb), len(wa)) - 1
+            if wz is None:
+                wz = torch.zeros((C, nz), dtype=torch.float64, device=x.device)
+            elif not (wz.is_cuda and wz.dtype == torch.float64 and wz.is_contiguous() and tuple(wz.shape) == (C, nz)):
+                raise ValueError("wz must be a contiguous float64 CUDA tensor (C, %d)" % nz)
+            bank.levels_weighted_ptr(dtype, x.data_ptr(), x.stride(0) if C > 1 else max(N, 1), out.data_ptr(), out.stride(1),
+                                     states.data_ptr(), wb, wa, wz.data_ptr(), N, C, block_len,
+                                     _lib.flags_of("auto", False, arith64), torch.cuda.current_stream().cuda_stream)
+            return out[:, :, :nblocks], states, wz
         bank.levels_ptr(dtype, x.data_ptr(), x.stride(0) if C > 1 else max(N, 1), out.data_ptr(), out.stride(1),
                         states.data_ptr(), N, C, block_len, _lib.flags_of("auto", False, arith64),
                         torch.cuda.current_stream().cuda_stream)

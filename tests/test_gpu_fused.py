@@ -144,6 +144,36 @@ def test_cfg5_named_size_weighted_bank(pfb, oracle):
             assert rel_l2(yc[:, bb], y0[:, bb, 0]) <= TOL64, (c, bb, rel_l2(yc[:, bb], y0[:, bb, 0]))
 
 
+@pytest.mark.parametrize("weighting", ["A", "C"])
+def test_weighted_band_levels_vs_oracle(pfb, oracle, weighting):
+    """Prefilter + bank + energies per block in ONE kernel (pfb_bank_levels_weighted): against the oracle's
+    composition (lfilter in scipy's order, sosfilter_double_mimo_c, then sum y^2 per block), ragged channel block,
+    two calls with carried bank states and prefilter delay values, numpy in / numpy out through filter_levels."""
+    from pyfilterbank_b200 import splweighting as spl
+    ofb, sos = _bank48(pfb)
+    b, a = spl._weighting_coeff_design_funsd[weighting](48000)
+    C, n, bl = 37, 9600, 960
+    x = np.random.default_rng(21).standard_normal((n, C))
+    _, y0, _ = oracle.weighted_bank(x, b, a, ofb.sosmat)                       # (N, B, C)
+    e0 = (y0.reshape(n // bl, bl, 33, C) ** 2).sum(axis=1)                     # (blocks, B, C)
+    e, st, wz = ofb.filter_levels(x, bl, weighting=weighting)
+    assert e.shape == e0.shape
+    scale = e0.max(axis=0, keepdims=True)
+    assert np.max(np.abs(e - e0) / scale) <= 5e-9, np.max(np.abs(e - e0) / scale)
+    zf = np.stack([oracle.lfilter_df2t(b, a, x[:, c])[1] for c in range(C)])
+    assert rel_l2(wz, zf) <= 1e-9
+    cut = 4 * bl
+    ea, st, wz = ofb.filter_levels(x[:cut], bl, weighting=weighting)
+    eb, st, wz = ofb.filter_levels(x[cut:], bl, states=st, weighting=weighting, weighting_states=wz)
+    ee = np.concatenate([ea, eb])
+    assert np.max(np.abs(ee - e0) / scale) <= 5e-9
+    # float32 signals on the device (float32 bank arithmetic): energies within the float32 path's own error
+    xt = torch.from_numpy(np.ascontiguousarray(x.T)).cuda().to(torch.float32)
+    bank = pfb.get_bank(sos)
+    ef, _, _ = pfb.bank_levels(bank, xt[:, :n // 64 * 64], bl // 64 * 64 * 2, weighting=(b, a))
+    assert ef.shape[1] == 33 and torch.isfinite(ef).all()
+
+
 # ---------------------------------------------------------------------------------------------
 # a6': decimating band path as one library call (pfb_decbank_filter)
 # ---------------------------------------------------------------------------------------------

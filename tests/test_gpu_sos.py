@@ -211,6 +211,12 @@ def test_f32_bank_modes(pfb, oracle):
         for b in range(B):
             ref_err = rel_l2(yf[:, b], yd[:, b])                          # the reference float path's own error
             assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (mode, b, ref_err)
+            # against the reference's own float32 output (sosfilt.c:5-28): north_star's 1e-4 wherever that output is
+            # itself meaningful (within 1e-5 of the double result: the bands from ~500 Hz up); below, the reference's
+            # float32 result is 1e-4 ... 4.5e-2 away from the double one and two float32 evaluations can only agree to
+            # the sum of their errors (bit-identity needs the exact kernel, asserted below)
+            bar = 1e-4 if ref_err <= 1e-5 else 11 * ref_err
+            assert rel_l2(y2[:, b], yf[:, b]) <= bar, (mode, b, ref_err, rel_l2(y2[:, b], yf[:, b]))
     y3, _ = pfb.bank_filter(bank, xt, mode="seq", exact=True)
     assert np.array_equal(y3.cpu().numpy(), yf)
 
