@@ -611,11 +611,6 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     tp.nb_a = nb;
     tp.levels = levels, tp.lev_ld = lev_ld, tp.lev_off = lev_off, tp.ut = ut;
     tp.wide = wide ? 1 : 0;
-    // Deep ring / two output tiles per band warp, one CTA per SM: an experiment for grids of about one CTA per SM.
-    // Measured slower than two resident CTAs of the standard shape in every case tried (cfg 5 at 1024 channels:
-    // 36.6-44.6 ms against 31.6-37.1 ms; cfg 3: 11.6 against 11.1 ms; profiles/r02c_cfg5_sweep.jsonl), so it is
-    // only reachable through PFB_TMA_DEEP=1.
-    tp.deep = env_int("PFB_TMA_DEEP", 0) != 0 && !wide && !levels && nb <= pfb::kTmaSmallBands ? 1 : 0;
     if (weighted) {
         tp.weighted = 1;
         tp.wnz = ex->wnz;

@@ -81,7 +81,7 @@ static void fill_tma_table(const TmaParams &p, const double *coef_host, CoefTabl
 template <int K, bool SCALED>
 static int run_tma_weighted(const TmaParams &p, const double *coef_host, const CUtensorMap &xmap, const CUtensorMap &ymap,
                             cudaStream_t s, int *launches, cudaEvent_t *ev, int phases) {
-    if (p.J != 1 || p.nb > kTmaWeightBands || p.wide || p.deep || p.dec_band1) return (int)cudaErrorInvalidValue;
+    if (p.J != 1 || p.nb > kTmaWeightBands || p.wide || p.dec_band1) return (int)cudaErrorInvalidValue;
     static thread_local CoefTable<PFB_A> tab;
     fill_tma_table<K, SCALED>(p, coef_host, tab);
     const unsigned grid = (unsigned)p.CB * (unsigned)p.G * (unsigned)p.NW;
@@ -125,7 +125,6 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e != cudaSuccess) return (int)e;
     if (p.weighted) return (int)cudaErrorInvalidValue;   // run_tma_weighted
-    if (p.deep && (NBMAX != kTmaSmallBands || p.wide)) return (int)cudaErrorInvalidValue;
     if (p.dec_band1 && (!PFB_HAS_DEC || p.levels || p.wide || p.weighted)) return (int)cudaErrorInvalidValue;
     static thread_local CoefTable<PFB_A> tab;
     fill_tma_table<K, SCALED>(p, coef_host, tab);
@@ -156,24 +155,7 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
             *launches += 1;
         }
         if (ev) cudaEventRecord(ev[2], s);
-        if (p.deep && !p.levels) {
-            // about one CTA per SM: deep input ring, two output tiles per band warp (small-band CTA shape only)
-            if constexpr (NBMAX == kTmaSmallBands) {
-                const int smem_d = (kTmaDeepStages + 2 * p.nb) * 2 * kTileBytes + 3 * kTmaDeepStages * 8;
-                auto launch_deep = [&](auto kern, int nthreads) -> cudaError_t {
-                    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d);
-                    if (e2 != cudaSuccess) return e2;
-                    kern<<<grid, nthreads, smem_d, s>>>(p, tab, xmap, ymap, ymap2);
-                    return cudaSuccess;
-                };
-#if PFB_HAS_DEC
-                if (p.dec_band1) e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, true>, threads);
-                else
-#endif
-                    e = launch_deep(sos_tma_deep_kernel<PFB_T, PFB_A, K, SCALED, false, false>, threads);
-                if (e != cudaSuccess) return (int)e;
-            }
-        } else if (p.dec_band1) {
+        if (p.dec_band1) {
 #if PFB_HAS_DEC
             auto kern_bd = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED, false, true>;
             e = cudaFuncSetAttribute(kern_bd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);

@@ -57,7 +57,6 @@ struct TmaParams {
     long long lev_ld, lev_off;
     int ut;
     int wide;             // output pass with 512-byte fragments (sos_tma_wide_kernel); L is then a multiple of 4 half rows
-    int deep;             // output pass with the deep ring / two output tiles per band warp (sos_tma_deep_kernel)
     // Fused SPL-weighting prefilter (WEIGHT kernels, splweighting.py:61-80): with one chunk per cascade a tile row is
     // a whole channel, so one extra warp runs the sequential transfer-function recurrence (scipy's operation
     // order, tf_step) in place on every input tile before the band warps read it -- the weighted signal never
@@ -435,7 +434,8 @@ __device__ __forceinline__ void weight_warp(const TmaParams &p, char *xs, uint64
 // WEIGHT: one more warp (index nbw + 1) runs the weighting prefilter on every input tile (weight_warp) and the
 // band warps wait for ITS barrier; DEC: the band p.dec_band1 - 1 stores decimated samples through ymap2.
 // YB: output tiles per band warp (2: a tile's stores drain while the next tile is filtered into the other buffer --
-// the deep variant for launches with about one CTA per SM, where nothing else hides the store and load latencies).
+// for kernels with one CTA per SM, where nothing else hides the store latency: the weighted kernel.  The same for the
+// plain J = 1 output pass was slower than two resident CTAs, profiles/r02c_cfg5_sweep.jsonl, and was removed).
 template <typename T, typename A, int K, int PASS, bool SCALED, int NH = 2, int NS = kTmaStages, bool WEIGHT = false,
           bool DEC = false, int YB = 1>
 __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &tab, const CUtensorMap &xmap,
@@ -891,19 +891,6 @@ sos_tma_weighted_kernel(const __grid_constant__ TmaParams p, const __grid_consta
                         const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
     extern __shared__ __align__(1024) char smem[];
     tma_cta<T, A, K, PASS, SCALED, 2, kTmaWeightStages, true, false, PASS == 1 ? 2 : 1>(p, tab, xmap, ymap, ymap, smem, blockIdx.x, 0);
-}
-
-// Output pass for launches with about one CTA per SM (one chunk per cascade and few (channel block, band group)
-// pairs: the many-channel configurations on a sharded bank): a deep input ring and two output tiles per band warp
-// hide the TMA load and store latencies that a second resident CTA would otherwise cover.
-constexpr int kTmaDeepStages = 8;
-template <typename T, typename A, int K, bool SCALED, bool WEIGHT, bool DEC>
-__global__ void __launch_bounds__((kTmaSmallBands + 1 + (WEIGHT ? 1 : 0)) * 32, 1)
-sos_tma_deep_kernel(const __grid_constant__ TmaParams p, const __grid_constant__ CoefTable<A> tab,
-                    const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
-                    const __grid_constant__ CUtensorMap ymap2) {
-    extern __shared__ __align__(1024) char smem[];
-    tma_cta<T, A, K, 1, SCALED, 2, kTmaDeepStages, WEIGHT, DEC, 2>(p, tab, xmap, ymap, ymap2, smem, blockIdx.x, 0);
 }
 
 // Carry between the two passes: per cascade, s[0] = carried-in state, s[j+1] = P s[j] + z[j];

@@ -60,7 +60,7 @@ def cfg3_full(C=1024, seconds=1):
     x = torch.randn(C, n, device="cuda", dtype=torch.float64) * 0.1
     y = torch.empty(C, B, n, device="cuda", dtype=torch.float64)
     ms = timeit(lambda: p.bank_filter(bank, x, None, out=y))
-    report("cfg3 1/12-oct order 6 full rate, %d ch x %d s f64%s" % (C, seconds, " deep=" + os.environ["PFB_TMA_DEEP"] if os.environ.get("PFB_TMA_DEEP") else ""),
+    report("cfg3 1/12-oct order 6 full rate, %d ch x %d s f64" % (C, seconds),
            ms, C * B * n, C * n * 8 * (B + 1),
            {"launch": bank.last_launch()})
 
@@ -72,8 +72,7 @@ def cfg3_dec(C=1024, seconds=4):
     load = float((1.0 / ofb.decimation_factors).sum())
     ms = timeit(lambda: ofb.filter_decimated(x), iters=2, warm=1)
     alg = C * n * 8 * (1 + load)
-    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s f64%s%s" % (C, seconds, " (unfused)" if os.environ.get("PFB_DEC_UNFUSED") else "",
-                                                                    " deep=" + os.environ["PFB_TMA_DEEP"] if os.environ.get("PFB_TMA_DEEP") else ""),
+    report("cfg3 1/12-oct order 6 DECIMATED, %d ch x %d s f64%s" % (C, seconds, " (unfused)" if os.environ.get("PFB_DEC_UNFUSED") else ""),
            ms, C * ofb.num_bands * n, alg, {"band_equivalents": load, "bands": ofb.num_bands, "dec": ofb._dec_bank().info()})
 
 
@@ -129,31 +128,23 @@ def cfg5(C=1024, seconds=5, dtype=torch.float64, fused=None):
     msw = timeit(lambda: spl.tf_filter(b, a, x.to(torch.float64)), iters=2, warm=1) if C <= 1024 else None
     report("cfg5 A-weighting + 1/3-oct bank, %d ch x %d s, %s, fused=%s nb=%s" % (
                C, seconds, "f64" if esz == 8 else "f32", fused, os.environ.get("PFB_TMA_NB", "auto")) +
-           (" deep=" + os.environ["PFB_TMA_DEEP"] if os.environ.get("PFB_TMA_DEEP") else "") +
            (" J=1" if os.environ.get("PFB_TMA_J") else ""), ms,
            C * B * n, C * n * esz * (B + 1), {"weighting_kernel_alone_ms": msw, "launch": info})
 
 
 def cfg5_sweep():
+    """Bands per CTA of the fused weighted bank (PFB_TMA_NB <= 9) and larger shards."""
     for dtype in (torch.float64, torch.float32):
         cfg5(dtype=dtype)                                  # planner's choice
         cfg5(dtype=dtype, fused=False)
-        for deep in ("0", "1"):
-            os.environ["PFB_TMA_DEEP"] = deep
-            for nb in (3, 4, 5, 7):
-                os.environ["PFB_TMA_NB"] = str(nb)
-                cfg5(dtype=dtype, fused=True)
-                torch.cuda.empty_cache()
+        for nb in (5, 7, 9):
+            os.environ["PFB_TMA_NB"] = str(nb)
+            cfg5(dtype=dtype, fused=True)
+            torch.cuda.empty_cache()
         os.environ.pop("PFB_TMA_NB", None)
-        os.environ.pop("PFB_TMA_DEEP", None)
         for C in (2048, 4096):
             cfg5(C=C, seconds=5 if C <= 2048 else 2, dtype=dtype)
             torch.cuda.empty_cache()
-    for deep in ("0", "1"):
-        os.environ["PFB_TMA_DEEP"] = deep
-        cfg3_dec(1024, 3)
-        cfg3_full(1024, 1)
-    os.environ.pop("PFB_TMA_DEEP", None)
 
 
 def cfg3_unfused(C=1024, seconds=3):
