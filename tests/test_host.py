@@ -110,6 +110,25 @@ def test_no_cpu_fallback():
     assert rc == -3 and b"no CPU fallback" in _lib.lib().pfb_last_error()
 
 
+def test_design_and_adapter_abi_validate_arguments():
+    """pfb_design_butter_sos / pfb_states_convert / pfb_bank_levels_weighted reject bad arguments before touching a device
+    (the reference raises for the same inputs: butterworth.py:44-47, :89); without a device the design call reports
+    PFB_ERR_NO_DEVICE instead of computing on the host."""
+    import torch
+    from pyfilterbank_b200 import _lib
+    L = _lib.lib()
+    v1, v2, out = np.array([0.1]), np.array([0.2]), np.empty((1, 4, 6))
+    assert L.pfb_design_butter_sos(2, 3, v1.ctypes.data, v2.ctypes.data, 1, out.ctypes.data, None, None) == -1   # odd L
+    assert L.pfb_design_butter_sos(7, 4, v1.ctypes.data, v2.ctypes.data, 1, out.ctypes.data, None, None) == -1   # kind
+    assert L.pfb_design_butter_sos(2, 4, v1.ctypes.data, None, 1, out.ctypes.data, None, None) == -1             # band-pass needs v2
+    assert L.pfb_design_butter_sos(2, 4, v1.ctypes.data, v2.ctypes.data, 1, None, None, None) == -1              # no output
+    assert L.pfb_states_convert(None, out.ctypes.data, 1, 1, 4, 0, 1, None) == -1
+    assert L.pfb_bank_levels_weighted(None, 1, None, 0, None, 0, None, None, 0, None, 0, None, 0, 0, 0, 0, None) == -1
+    if not torch.cuda.is_available():
+        assert L.pfb_design_butter_sos(2, 4, v1.ctypes.data, v2.ctypes.data, 1, out.ctypes.data, None, None) == -3
+        assert b"no CUDA device" in L.pfb_last_error()
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "pyfilterbank_b200")
     for dirpath, _, files in os.walk(pkg):
