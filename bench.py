@@ -283,8 +283,8 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         d = {"value": world * units_per_rank / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-             "roofline_frac": alg_bytes_per_rank / (ms * 1e-3) / 1e9 / peak,
-             "algorithmic_GB_per_gpu": alg_bytes_per_rank / 1e9}
+             "roofline_frac": None if alg_bytes_per_rank is None else alg_bytes_per_rank / (ms * 1e-3) / 1e9 / peak,
+             "algorithmic_GB_per_gpu": None if alg_bytes_per_rank is None else alg_bytes_per_rank / 1e9}
         d.update(extra)
         out[name] = d
 
@@ -320,11 +320,11 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
                     for _ in range(blocks):
                         pfb.bank_levels(bank, x, 4800, st, weighting=(b, a), wz=wz)
                 ms = event_time(torch, run_lev, 2, 1)
-                finish("cfg5_f32_levels", ms, C * B * nblk * blocks, C * nblk * blocks * esz,
+                finish("cfg5_f32_levels", ms, C * B * nblk * blocks, None,
                        {"workload": "A-weighting + 1/3-octave bank + band energies per 0.1 s in one kernel "
-                                    "(pfb_bank_levels_weighted), %d of 8192 channels per GPU, %d blocks of 0.5 s, float32: "
-                                    "only the input is read (roofline_frac counts those bytes; the kernel is FP32/FP64-issue "
-                                    "bound)" % (C, blocks)})
+                                    "(pfb_bank_levels_weighted), %d of 8192 channels per GPU, %d blocks of 0.5 s, float32" % (C, blocks),
+                        "bound": "FP32 / FP64 issue: only the input (%.2f GB per GPU) is read, no band signal is written, so "
+                                 "there is no HBM roofline for it" % (C * nblk * blocks * esz / 1e9)})
                 y = None
             del x, y, st, wz
             torch.cuda.empty_cache()

@@ -17,6 +17,21 @@ except Exception:
     pass
 
 
+LAST_CLOCK = {}
+
+
+def _sm_clock():
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        return {"sm_mhz": pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                "power_w": pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                "throttle": hex(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))}
+    except Exception as e:   # the clock is context, not the measurement
+        return {"error": repr(e)[:80]}
+
+
 def timeit(fn, iters=3, warm=2):
     for _ in range(warm):
         fn()
@@ -26,6 +41,7 @@ def timeit(fn, iters=3, warm=2):
     for _ in range(iters):
         fn()
     e1.record()
+    LAST_CLOCK.update(_sm_clock())        # sampled while the last kernels are still running
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
 
@@ -35,6 +51,7 @@ def report(name, ms, units, alg_bytes, extra=None):
          "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / PEAK}
     if extra:
         d.update(extra)
+    d["clock_during_run"] = dict(LAST_CLOCK)
     print(json.dumps(d), flush=True)
 
 
