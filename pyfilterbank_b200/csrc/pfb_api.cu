@@ -604,6 +604,7 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     pfb::TmaParams tp{};
     tp.zs = ws.first;
     tp.states = states;
+    tp.y = y, tp.ldy = ldy, tp.By = By;
     tp.L = Lt;
     tp.Q = Q, tp.B = b->B, tp.C = C, tp.J = J, tp.nb = nb, tp.G = G;
     tp.JR = JR, tp.CH = CH, tp.NW = J / JR, tp.CB = (C + CH - 1) / CH;

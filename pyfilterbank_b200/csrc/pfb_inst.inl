@@ -101,7 +101,7 @@ static int run_tma_weighted(const TmaParams &p, const double *coef_host, const C
         if (e != cudaSuccess) return (int)e;
         kern<<<grid, threads, smem_in, s>>>(p, tab, xmap, ymap);
     } else {
-        const int smem = smem_in + 2 * p.nb * 2 * kTileBytes;
+        const int smem = smem_in + 2 * p.nb * out_tile_bytes<PFB_T, PFB_A>(2, false, true);
         auto kern = sos_tma_weighted_kernel<PFB_T, PFB_A, K, 1, SCALED>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -119,7 +119,8 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
     auto kern_b = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED>;
     auto kern_l = sos_tma_kernel<PFB_T, PFB_A, K, 2, NBMAX, SCALED>;
     const int smem_a = kTmaStages * 2 * kTileBytes + 3 * kTmaStages * 8;
-    const int smem_b = (kTmaStages + p.nb) * 2 * kTileBytes + 3 * kTmaStages * 8;
+    const int smem_b = kTmaStages * 2 * kTileBytes + p.nb * out_tile_bytes<PFB_T, PFB_A>(2, false, false) + 3 * kTmaStages * 8;
+    const int smem_bd = kTmaStages * 2 * kTileBytes + p.nb * out_tile_bytes<PFB_T, PFB_A>(2, true, false) + 3 * kTmaStages * 8;
     cudaError_t e = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_l, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
@@ -158,15 +159,15 @@ static int run_tma_ns(const TmaParams &p, const double *coef_host, const CUtenso
         if (p.dec_band1) {
 #if PFB_HAS_DEC
             auto kern_bd = sos_tma_kernel<PFB_T, PFB_A, K, 1, NBMAX, SCALED, false, true>;
-            e = cudaFuncSetAttribute(kern_bd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
+            e = cudaFuncSetAttribute(kern_bd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bd);
             if (e != cudaSuccess) return (int)e;
-            kern_bd<<<grid, threads, smem_b, s>>>(p, tab, xmap, ymap, ymap2);
+            kern_bd<<<grid, threads, smem_bd, s>>>(p, tab, xmap, ymap, ymap2);
 #endif
         } else if (p.levels) {
             kern_l<<<grid, threads, smem_a, s>>>(p, tab, xmap, ymap, ymap2);   // energies instead of band signals
         } else if (p.wide) {
             auto kern_w = sos_tma_wide_kernel<PFB_T, PFB_A, K, SCALED>;
-            const int smem_w = (2 + p.nb) * 4 * kTileBytes + 3 * 2 * 8;
+            const int smem_w = 2 * 4 * kTileBytes + p.nb * out_tile_bytes<PFB_T, PFB_A>(4, false, false) + 3 * 2 * 8;
             e = cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w);
             if (e != cudaSuccess) return (int)e;
             kern_w<<<grid, threads, smem_w, s>>>(p, tab, xmap, ymap);

@@ -71,6 +71,11 @@ struct TmaParams {
     // in dec_states [C][Ktot][2]; the states array then holds Bs = B - 1 bands (Bs == 0 means B).
     int dec_band1, dec_phase, Bs;
     void *dec_states;
+    // Output pass: every lane copies its own row fragment to global memory with a one-dimensional bulk copy
+    // (tma_cta, kBulkRows): y base, row pitch in elements, bands stored through it (B, or B - 1 with a decimating band)
+    void *y;
+    long long ldy;
+    int By;
     // PFB_WARP_PROF builds only: clocks per warp role, [warp index][0 wait for input, 1 arithmetic, 2 wait for the
     // output buffer, 3 total, 4 proxy fence + warp sync, 5 barrier arrive + store issue], summed over CTAs (lane 0's clock64)
     unsigned long long *prof;
@@ -206,6 +211,30 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
                  "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// one-dimensional bulk copy shared -> global of `bytes` (multiple of 16) contiguous bytes, this thread's bulk group
+__device__ __forceinline__ void bulk_store_1d(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes)
+                 : "memory");
+}
+// Output tile of one band warp when the lanes copy their own rows (kBulkRows): 32 rows of NH * 128 bytes, 16 bytes of
+// padding per row (a lane-per-row writer with 16-byte stores then needs the minimum of four shared-memory wavefronts),
+// slots 1024-byte aligned so that the decimating band can keep its swizzled tensor-store tile in the same slot.
+__host__ __device__ constexpr int out_row_stride(int NH) { return NH * kRowBytes + 16; }
+__host__ __device__ constexpr int out_slot_bytes(int NH) { return (32 * out_row_stride(NH) + 1023) / 1024 * 1024; }
+// Which output passes copy rows per lane (see tma_cta), and the shared memory of one band warp's output tile
+#ifndef PFB_BULK_ROWS
+#define PFB_BULK_ROWS -1     // -1: per kernel (below); 0 / 1: never / always (A/B builds, profiles/r03d_bulk_rows.txt)
+#endif
+template <typename T, typename A>
+__host__ __device__ constexpr bool bulk_rows(int NH, bool dec, bool weight) {
+    if (dec) return false;     // the decimating band keeps its swizzled tensor-store tile in the same slot
+    if (PFB_BULK_ROWS >= 0) return PFB_BULK_ROWS != 0;
+    return !weight && NH == 4 && sizeof(T) == 8 && sizeof(A) == 8;      // the wide float64 output pass
+}
+template <typename T, typename A>
+__host__ __device__ constexpr int out_tile_bytes(int NH, bool dec, bool weight) {
+    return bulk_rows<T, A>(NH, dec, weight) ? out_slot_bytes(NH) : NH * kTileBytes;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
@@ -287,7 +316,8 @@ __device__ __forceinline__ void cascade_wave(const T *e, const A (&c)[K][5], A (
 // (output-type rounded) results are added to `acc` (band-level epilogue).
 template <typename T, typename A, int K, int MODE, bool SCALED>
 __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int key, const A (&c)[K][5], A (&w)[K][2],
-                                            A *acc = nullptr) {
+                                            A *acc = nullptr, int okey = -1) {
+    if (okey < 0) okey = key;      // swizzle key of the output row (0: linear row of the bulk-row layout)
     constexpr bool STORE = MODE == 1;
     using V = typename Vec16<T>::type;
     constexpr int EPV = Vec16<T>::N;
@@ -308,7 +338,7 @@ __device__ __forceinline__ void filter_half(const char *xrow, char *yrow, int ke
         });
         if (STORE) {
 #pragma unroll
-            for (int v = 0; v < kBatch; ++v) *reinterpret_cast<V *>(yrow + (((v0 + v) ^ key) << 4)) = in[v];
+            for (int v = 0; v < kBatch; ++v) *reinterpret_cast<V *>(yrow + (((v0 + v) ^ okey) << 4)) = in[v];
         }
     }
 }
@@ -464,8 +494,22 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     const int nb_here = min(nbw, p.B - b0);
 
     char *xs = smem;                                          // [stages][2][tile]
-    char *ys = smem + NS * kStageBytes;               // [nb][2][tile], output pass only
-    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb * YB : 0) * kStageBytes);
+    // Output pass: the lanes copy their own row fragments (NH * 128 contiguous bytes each) to global memory with
+    // one-dimensional bulk copies instead of lane 0 issuing NH tensor stores of [32 rows x 128 B].  Measured on the
+    // store pattern alone (scripts/ubench/tma_store_rows.cu, profiles/r02z_ubench_store_rows.txt): 6.5-6.7 TB/s for
+    // 256- and 512-byte fragments against 4.8-5.3 / 5.7 TB/s with tensor stores (contiguous writes: 6.8 TB/s), and the
+    // issue is one instruction of the whole warp instead of 150-400 clocks of lane 0 per store.
+    // In the kernels the copy instruction of a warp carries 32 requests and occupies the warp for 1500-2200 clocks per
+    // tile (profiles/r03b_warp_prof.txt) where two tensor stores cost 270: a gain only where a tile is long in samples
+    // and the pass is bound by the stores -- the wide float64 kernel (cfg 2 output pass 10.02 -> 9.67 ms).  A/B builds
+    // on one box (profiles/r03d_bulk_rows.txt): the order-6 bank (11.0 -> 12.5 ms), the fused weighted bank (f32 9.3 ->
+    // 12.5 ms), the float32 wide kernel (6.27 -> 6.86 ms) and float32 signals with float64 arithmetic (10.23 -> 10.54
+    // ms) lose with it and keep the tensor stores.
+    constexpr bool kBulkRows = STORE_Y && bulk_rows<T, A>(NH, DEC, WEIGHT);
+    constexpr int kRowStride = out_row_stride(NH);
+    constexpr unsigned kSlotBytes = kBulkRows ? (unsigned)out_slot_bytes(NH) : kStageBytes;
+    char *ys = smem + NS * kStageBytes;               // [nb][YB][slot], output pass only
+    uint64_t *full = reinterpret_cast<uint64_t *>(ys + (STORE_Y ? p.nb * YB : 0) * kSlotBytes);
     uint64_t *empty = full + NS;
     uint64_t *wfull = empty + NS;                             // WEIGHT kernels: weighting warp -> band warps
     uint64_t *in_bar = WEIGHT ? wfull : full;                 // what a band warp waits for
@@ -571,8 +615,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         if (wt > nt) wt = nt;
         t_mine = (int)(nt - wt);
     }
-    char *ybuf = ys + slot * YB * kStageBytes;
-    char *yrow = ybuf + lane * kRowBytes;
+    char *ybuf = ys + slot * YB * kSlotBytes;
+    char *yrow = ybuf + lane * kRowBytes;               // swizzled tensor-store tile (decimating band)
 
     if (PASS == 2) {
         double acc_unit = 0.0;
@@ -604,7 +648,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             const unsigned ph = (unsigned)((t / NS) & 1);
             mbar_wait_warp(&in_bar[s], ph, lane);
             const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
-            const int yb = YB > 1 ? (int)(t % YB) * (int)kStageBytes : 0;
+            const int yb = YB > 1 ? (int)(t % YB) * (int)kSlotBytes : 0;
             if (lane == 0) bulk_wait_read_upto(YB - 1);          // one bulk group per tile
             __syncwarp();
 #pragma unroll 1
@@ -621,6 +665,38 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                 bulk_commit();
             }
         }
+    } else if (PASS_B && kBulkRows) {
+        PROF_DECL;
+        // this lane's output row in global memory and in the warp's output slot
+        const int By = p.By ? p.By : p.B;
+        char *grow = reinterpret_cast<char *>(p.y) +
+                     (((size_t)(row_ok ? chn : 0) * By + band) * (size_t)p.ldy + (size_t)j * (size_t)p.L) * sizeof(T);
+        char *orow = ybuf + lane * kRowStride;
+        for (long long t = 0; t < nt; ++t) {
+            const int s = (int)(t % NS);
+            const unsigned ph = (unsigned)((t / NS) & 1);
+            mbar_wait_warp(&in_bar[s], ph, lane);
+            PROF_LAP(0);
+            const char *xrow = xs + s * kStageBytes + lane * kRowBytes;
+            const int yb = YB > 1 ? (int)(t % YB) * (int)kSlotBytes : 0;
+            // the row is overwritten once this lane's copy of tile t - YB has been read out of shared memory
+            bulk_wait_read_upto(YB - 1);
+            PROF_LAP(2);
+            // The half rows stay a loop: fully unrolled, the wide float32 tile is ~24 KB of code per warp iteration and
+            // stalls on instruction fetch.
+#pragma unroll 1
+            for (int h = 0; h < NH; ++h)
+                filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, orow + yb + h * kRowBytes, key, c, wst, nullptr, 0);
+            PROF_LAP(1);
+            fence_proxy_async();      // this lane's row -> async proxy; also orders the tile's loads before the release
+            if (row_ok) bulk_store_1d(grow + (size_t)t * (NH * kRowBytes), orow + yb, NH * kRowBytes);
+            bulk_commit();
+            PROF_LAP(5);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            PROF_LAP(4);
+        }
+        PROF_END(p, slot, lane);
     } else if (PASS_B) {
         PROF_DECL;
         for (long long t = 0; t < nt; ++t) {
@@ -638,7 +714,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
             // stalls on instruction fetch; and with the warp-level waits above (real WARPSYNCs in the loop) every
             // fully unrolled variant lost 40-100 % (float64 cfg 2 output pass 15.8 vs 10.0 ms, cfg 3 21.9 vs 11.2 ms,
             // profiles/r01h_wait_variants.txt), while the rolled loop costs nothing measurable.
-            const int yb = YB > 1 ? (int)(t % YB) * (int)kStageBytes : 0;
+            const int yb = YB > 1 ? (int)(t % YB) * (int)kSlotBytes : 0;
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
                 // (YB buffers: the groups of the YB - 1 tiles in between may still be pending)
@@ -691,7 +767,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
         }
     }
     if (PASS_B) {
-        if (STORE_Y && lane == 0) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
+        if (STORE_Y && (kBulkRows || lane == 0)) bulk_wait0();     // outstanding stores must complete before the CTA's smem goes away
         if (row_ok && j == p.J - 1) {    // the last chunk ends with the cascade's final state
             A *st = cascade_states<A>(p, chn, band);
 #pragma unroll

@@ -35,6 +35,31 @@ __global__ void __launch_bounds__(256) tma_wr(const __grid_constant__ CUtensorMa
     }
 }
 
+// The same store pattern with ONE-DIMENSIONAL bulk copies: every lane copies its own row fragment (FRAG contiguous
+// bytes, shared -> global) with cp.async.bulk, all 32 lanes in one instruction; rows are FRAG + 16 bytes apart in shared
+// memory (what a lane-per-row writer needs to stay free of bank conflicts).  32 requests of FRAG bytes per step instead
+// of FRAG / 128 tensor requests of 32 x 128 bytes issued by one lane.
+template <int FRAG>
+__global__ void __launch_bounds__(256) bulk1d_wr(double *y, long long L, long long n, int groups) {
+    extern __shared__ __align__(1024) char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int RS = FRAG + 16;
+    char *buf = smem + warp * 32 * RS;
+    for (int i = lane; i < 32 * RS / 8; i += 32) reinterpret_cast<double *>(buf)[i] = 1.0;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncwarp();
+    const int q = (blockIdx.x / groups) * 8 + warp, w = blockIdx.x % groups;
+    char *dst = reinterpret_cast<char *>(y + (size_t)q * n + (size_t)(32 * w + lane) * L);
+    const uint32_t src = smem_addr(buf + lane * RS);
+    const long long nt = L * 8 / FRAG;
+    for (long long t = 0; t < nt; ++t) {
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst + t * FRAG), "r"(src), "r"(FRAG) : "memory");
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+
 // HINT: 1 evict_first, 2 evict_last, 3 evict_unchanged (createpolicy.fractional), BOXES boxes per step
 template <int BOXES, int HINT>
 __global__ void __launch_bounds__(256) tma_wr_hint(const __grid_constant__ CUtensorMap ymap, long long L, int groups, int) {
@@ -132,6 +157,20 @@ int main(int argc, char **argv) {
         printf("evict_last:      "); run(tma_wr_hint<2, 2>, 2);
         printf("evict_unchanged: "); run(tma_wr_hint<2, 3>, 2);
         printf("evict_last 512:  "); run(tma_wr_hint<4, 2>, 4);
+        auto run1d = [&](auto kern, int frag) {
+            const int smem = 8 * 32 * (frag + 16);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            float best = 1e9;
+            for (int it = 0; it < 3; ++it) {
+                cudaEventRecord(e0);
+                kern<<<Q / 8 * groups, 256, smem>>>(y, L, n, groups);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+            }
+            printf("1-D bulk copy per lane  J=%3d  fragment %4d B: %7.3f ms  %.0f GB/s  (%s)\n", J, frag, best, bytes / (best * 1e-3) / 1e9,
+                   cudaGetErrorString(cudaGetLastError()));
+        };
+        run1d(bulk1d_wr<128>, 128); run1d(bulk1d_wr<256>, 256); run1d(bulk1d_wr<512>, 512); run1d(bulk1d_wr<1024>, 1024);
         for (int vb : {16, 32}) {
             float best = 1e9;
             for (int it = 0; it < 3; ++it) {
