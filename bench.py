@@ -256,17 +256,33 @@ def cpu_extra_baselines(sos, seconds=2):
     return out
 
 
-def event_time(torch, fn, iters, warm):
+LAST_RUNS = {}
+
+
+def event_time(torch, fn, iters, warm, reps=2):
+    """Mean time of `iters` calls between CUDA events after `warm` untimed calls, measured `reps` times with the SM clock
+    and throttle reasons sampled meanwhile; returns the fastest repetition and leaves all of them in LAST_RUNS (these
+    extra configs run once each, right after other heavy work: a single disturbed measurement would otherwise stand)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    runs = []
+    for _ in range(reps):
+        sampler = ClockSampler(torch.cuda.current_device())
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        clk = sampler.stop(t0, t1)
+        runs.append({"ms": e0.elapsed_time(e1) / iters, "sm_mhz": clk.get("sm_mhz"), "reasons": clk.get("reasons")})
+    LAST_RUNS.clear()
+    LAST_RUNS["runs"] = runs
+    return min(r["ms"] for r in runs)
 
 
 def other_configs(torch, pfb, dist, dev, rank, world, peak):
@@ -286,6 +302,7 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
              "roofline_frac": None if alg_bytes_per_rank is None else alg_bytes_per_rank / (ms * 1e-3) / 1e9 / peak,
              "algorithmic_GB_per_gpu": None if alg_bytes_per_rank is None else alg_bytes_per_rank / 1e9}
         d.update(extra)
+        d["runs"] = list(LAST_RUNS.get("runs", []))     # every repetition (this rank) with its clocks; ms_per_step = fastest
         out[name] = d
 
     gen = torch.Generator(device=dev)
@@ -306,7 +323,7 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
             def run():
                 for _ in range(blocks):      # consecutive blocks of the stream: states and delay values carried
                     pfb.bank_filter_weighted(bank, x, b, a, st, wz, out=y)
-            ms = event_time(torch, run, 2, 1)
+            ms = event_time(torch, run, 2, 2)
             finish(name, ms, C * B * nblk * blocks, C * nblk * blocks * esz * (B + 1),
                    {"workload": "A-weighting + 1/3-octave bank, %d of 8192 channels per GPU, %d blocks of 0.5 s @ 48 kHz "
                                 "with carried states, %s" % (C, blocks, "float32" if esz == 4 else "float64"),
@@ -319,7 +336,7 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
                 def run_lev():
                     for _ in range(blocks):
                         pfb.bank_levels(bank, x, 4800, st, weighting=(b, a), wz=wz)
-                ms = event_time(torch, run_lev, 2, 1)
+                ms = event_time(torch, run_lev, 2, 2)
                 finish("cfg5_f32_levels", ms, C * B * nblk * blocks, None,
                        {"workload": "A-weighting + 1/3-octave bank + band energies per 0.1 s in one kernel "
                                     "(pfb_bank_levels_weighted), %d of 8192 channels per GPU, %d blocks of 0.5 s, float32" % (C, blocks),
@@ -341,7 +358,7 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
         def run():
             bands, state[0] = ofb.filter_decimated(x, state[0])
             del bands
-        ms = event_time(torch, run, 2, 1)
+        ms = event_time(torch, run, 2, 2)
         info = ofb._dec_bank().info()
         finish("cfg3_decimated", ms, C * ofb.num_bands * nblk, C * nblk * 8 * (1 + load),
                {"workload": "1/12-octave order-6 bank, per-band decimation, %d of 1024 channels per GPU, 3 s blocks "
@@ -356,7 +373,7 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
         gfb = gt.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
         Bg, C, n = len(gfb.centerfrequencies), 512 // world, 160000
         x = torch.randn((C, n), generator=gen, device=dev, dtype=torch.float64) * 0.1
-        ms = event_time(torch, lambda: gt.fos_bank(x, gfb._coef_rows, 4), 2, 1)
+        ms = event_time(torch, lambda: gt.fos_bank(x, gfb._coef_rows, 4), 2, 2)
         finish("cfg4_gammatone", ms, C * Bg * n, C * n * (8 + 16 * Bg),
                {"workload": "gammatone order 4, %d ERB bands, %d of 512 signals x 10 s @ 16 kHz per GPU, complex128 out" % (Bg, C)})
         del x

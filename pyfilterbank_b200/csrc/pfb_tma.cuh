@@ -139,6 +139,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
 // control flow, or it treats the code behind a single-lane spin as converged (see mbar_wait_warp).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     while (!mbar_try_wait(bar, parity)) {
+#if PFB_PRODUCER_BACKOFF
+        __nanosleep(PFB_PRODUCER_BACKOFF);     // the producer is never latency critical (the ring is full when it waits)
+#endif
     }
 }
 // Wait of a whole consumer warp: every lane tests the phase (no branch inside the asm) and a warp vote ends the loop
@@ -279,6 +282,9 @@ __device__ __forceinline__ A section_step(A x, const A *c, A &w1, A &w2) {
 #endif
 #ifndef PFB_W_ROLLED
 #define PFB_W_ROLLED 0
+#endif
+#ifndef PFB_PRODUCER_BACKOFF
+#define PFB_PRODUCER_BACKOFF 0     // nanoseconds between the producer lane's polls of an `empty` barrier (experiment)
 #endif
 #ifndef PFB_ONE_COMMIT
 #define PFB_ONE_COMMIT -1    // output pass, bulk groups: 1 = one per tile, 0 = one per 128-byte half row, -1 = per kernel (below)

@@ -78,13 +78,20 @@ __global__ void __launch_bounds__(512) probe(const __grid_constant__ Coef cf, co
         }
     }
     long long t1 = clock64();
-    if ((threadIdx.x & 31) == 0) clk[blockIdx.x * 16 + warp] = t1 - t0;
+    if ((threadIdx.x & 31) == 0) {
+        clk[blockIdx.x * 16 + warp] = t1 - t0;
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        if (blockIdx.x == 0) clk[16 * 4096 + warp] = wid;      // hardware warp slot of this warp (CTA 0)
+    }
     if (acc == 123.456) sink[0] = acc;
 }
 
-static void run(const char *label, const char *roles, int ctas_per_sm, int sms) {
+__global__ void shifter(double *sink) { if (sink[0] == 123.456) sink[1] = 1; }
+
+static void run(const char *label, const char *roles, int ctas_per_sm, int sms, int shift_warps = 0) {
     static char *d_roles = nullptr; static long long *d_clk = nullptr; static double *d_sink = nullptr;
-    if (!d_roles) { cudaMalloc(&d_roles, 16); cudaMalloc(&d_clk, 8 * 16 * 4096); cudaMalloc(&d_sink, 8); }
+    if (!d_roles) { cudaMalloc(&d_roles, 16); cudaMalloc(&d_clk, 8 * 16 * 4096 + 8 * 16); cudaMalloc(&d_sink, 8); }
     Coef cf;
     for (int i = 0; i < 8; ++i) { cf.b[i] = 0.1 + 0.01 * i; cf.a[i] = 0.05 - 0.01 * i; }
     for (int k = 0; k < 4; ++k) { cf.c[k][0] = 0.5; cf.c[k][1] = 0.3; cf.c[k][2] = -0.2; cf.c[k][3] = -0.4; cf.c[k][4] = 0.1; }
@@ -93,18 +100,24 @@ static void run(const char *label, const char *roles, int ctas_per_sm, int sms) 
     cudaMemset(d_clk, 0, 8 * 16 * 4096);
     const int n = 20000, grid = sms * ctas_per_sm;
     probe<<<grid, nw * 32>>>(cf, d_roles, 64, d_clk, d_sink);
+    if (shift_warps) shifter<<<sms, 32 * shift_warps>>>(d_sink);     // moves the SMs' warp-slot allocation on by a few slots
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     probe<<<grid, nw * 32>>>(cf, d_roles, n, d_clk, d_sink);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    static long long h[16 * 4096];
+    static long long h[16 * 4096 + 16];
     cudaMemcpy(h, d_clk, 8 * 16 * grid, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h + 16 * 4096, d_clk + 16 * 4096, 8 * 16, cudaMemcpyDeviceToHost);
     printf("%-34s roles %-14s CTAs/SM %d  %.3f ms | clk/sample per warp:", label, roles, ctas_per_sm, ms);
     for (int w = 0; w < nw; ++w) {
         double worst = 0;
         for (int c = 0; c < grid; ++c) worst = worst > h[c * 16 + w] ? worst : (double)h[c * 16 + w];
         if (roles[w] == '.') printf("   -"); else printf(" %4.0f", worst / n);
+    }
+    if (shift_warps) {
+        printf("   | after a %d-warp kernel; hw warp slots of CTA 0:", shift_warps);
+        for (int w = 0; w < nw; ++w) printf(" %lld", h[16 * 4096 + w]);
     }
     printf("\n");
 }
@@ -146,5 +159,8 @@ int main() {
     run("own port: 3 bands, W at 3, 4 CTAs", "BBBW", 4, sms);
     run("12 bands, no W", "BBBBBBBBBBBB", 1, sms);
     run("11 bands + W at 11", "BBBBBBBBBBBW", 1, sms);
+    // does the role -> sub-partition map survive other kernels (warp slots are handed out from a moving position)?
+    for (int sh = 1; sh <= 4; ++sh) run("own port, 12 warps, shifted", "DDDWDDD.DDD.", 1, sms, sh);
+    for (int sh = 1; sh <= 4; ++sh) run("own port, 11 warps, shifted", "DDDWDDD.DDD", 1, sms, sh);
     return 0;
 }
