@@ -285,7 +285,7 @@ def event_time(torch, fn, iters, warm, reps=2):
     return min(r["ms"] for r in runs)
 
 
-def other_configs(torch, pfb, dist, dev, rank, world, peak):
+def other_configs(torch, pfb, dist, dev, rank, world, peak, with_cpu=True):
     """Per-GPU shards of BASELINE.json configs[2..4] (extra keys; the headline is configs[1]): channels / signals
     are sharded over the ranks, long signals stream in time blocks with carried states, inputs are generated on the
     device.  Each entry: band-samples/s over all ranks (max time over ranks) and the fraction of the HBM roofline
@@ -369,6 +369,39 @@ def other_configs(torch, pfb, dist, dev, rank, world, peak):
         torch.cuda.empty_cache()
     except Exception as e:
         out["cfg3_error"] = repr(e)[:300]
+    if rank == 0:
+        try:   # cfg 1: the reference's own CPU-runnable case through the reference-facing call, numpy in / numpy out
+            ofb1 = pfb.FractionalOctaveFilterbank()                         # fs 44100, order 4, 1/3 octave, 33 bands
+            x1 = np.random.default_rng(0).standard_normal(441000)
+            for _ in range(3):
+                ofb1.filter_mimo_c(x1)
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                y1, _ = ofb1.filter_mimo_c(x1)
+                ts.append(time.perf_counter() - t0)
+            xt = torch.from_numpy(x1).to(dev).reshape(-1, 1)
+            ms_dev = event_time(torch, lambda: ofb1.filter_mimo_c(xt), 3, 2)
+            d = {"value": 441000 * 33 / min(ts), "unit": UNIT, "ms_per_call": min(ts) * 1e3, "ms_per_call_all": [t * 1e3 for t in ts],
+                 "device_resident_ms": ms_dev, "h2d_bytes": 441000 * 8, "d2h_bytes": 441000 * 33 * 8,
+                 "workload": "FractionalOctaveFilterbank() default (fs 44100, order 4, 33 bands), 1 channel x 10 s white noise, "
+                             "float64, filter_mimo_c(numpy) -> numpy: host-to-device copy, kernels, device-to-host copy of the "
+                             "(N, B, C) result included (rank 0 only)"}
+            try:   # the same call on the CPU checker (one core, like the reference's own wrapper + C loop)
+                if not with_cpu:
+                    raise RuntimeError("--no-cpu")
+                from oracle import oracle as o
+                t0 = time.perf_counter()
+                o.sosfilter_double_mimo_c(x1, ofb1.sosmat, use_ref=o.have_ref())
+                d["cpu_same_call_ms"] = (time.perf_counter() - t0) * 1e3
+                d["cpu_kind"] = "oracle wrapper restatement + " + ("oracle/_ref sosfilter_double_mimo" if o.have_ref() else "oracle port")
+            except Exception as e:
+                d["cpu_same_call_ms"] = None
+                d["cpu_error"] = repr(e)[:200]
+            out["cfg1_default_bank"] = d
+            del xt
+        except Exception as e:
+            out["cfg1_error"] = repr(e)[:300]
     try:   # cfg 4: gammatone, 64 ERB bands, 512 signals x 10 s @ 16 kHz sharded over the ranks
         gfb = gt.GammatoneFilterbank(samplerate=16000, order=4, startband=-14, endband=18, density=0.5)
         Bg, C, n = len(gfb.centerfrequencies), 512 // world, 160000
@@ -701,7 +734,7 @@ def main():
             pass
         del x
         torch.cuda.empty_cache()
-        configs = other_configs(torch, pfb, dist, dev, rank, world, peak)
+        configs = other_configs(torch, pfb, dist, dev, rank, world, peak, with_cpu=not args.no_cpu)
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:

@@ -924,8 +924,8 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         // (few channels: the wide kernel's one CTA per SM leaves SMs idle -- measured slower below ~24 channels,
         // scripts/wide_probe.py -- so it needs enough (channel, band group) pairs for two CTAs per SM at J <= 128)
         const int Gw = (b->B + pfb::kTmaMaxBands - 1) / pfb::kTmaMaxBands;
-        const bool same_arith = dtype == PFB_F64 || !arith64;   // float64 / float64 or float32 / float32
-        bool wide = same_arith && b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
+        // (float32 signals with float64 arithmetic too: 10.24 -> 9.31 ms per cfg 2 step, profiles/r03h_fd_wide.txt)
+        bool wide = b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
         if (ex) wide = false;               // the fused stages live in the 256-byte-fragment kernel
         if (ex && ex->wnz) {
