@@ -354,7 +354,7 @@ static int run_fos_tma_nx(const FosTmaParams &p, const FosCoef &tab, const TmaPa
     auto ka = fos_tma_kernel<ORDER, false, NX>;
     auto kb = fos_tma_kernel<ORDER, true, NX>;
     const int smem_a = kFosStages * NX * kTileBytes + 2 * kFosStages * 8;
-    const int smem_b = (kFosStages * NX + 2 * NX * p.nb) * kTileBytes + 2 * kFosStages * 8;
+    const int smem_b = kFosStages * NX * kTileBytes + p.nb * (NX == 2 ? out_slot_bytes(2 * NX) : 2 * NX * kTileBytes) + 2 * kFosStages * 8;
     cudaError_t e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     if (e != cudaSuccess) return (int)e;
@@ -444,6 +444,7 @@ int launch_fos_tma(const double *x, long long ldx, double *y, long long ldy, con
     p.L = Lt;
     p.Q = (int)Q, p.B = B, p.C = C, p.J = J, p.JR = JR, p.CH = CH, p.NW = J / JR, p.CB = (C + CH - 1) / CH;
     p.nb = nb, p.G = G;
+    p.y = y, p.ldy2 = 2 * ldy;
     TmaParams cp{};
     void *scratch = nullptr;
     cudaError_t e = cudaSuccess;

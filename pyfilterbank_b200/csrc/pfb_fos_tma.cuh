@@ -24,6 +24,8 @@ struct FosTmaParams {
     const int *warm;      // [B] pre-pass samples per chunk
     long long L;
     int Q, B, C, J, JR, CH, NW, CB, nb, G;
+    double *y;            // output base and row pitch in doubles (2 per complex sample): the wide output pass copies every
+    long long ldy2;       // lane's own 512-byte row fragment with a one-dimensional bulk copy (like sos_tma_wide_kernel)
 };
 
 struct FosCoef {
@@ -56,7 +58,9 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
     extern __shared__ __align__(1024) char smem[];
     constexpr int TLEN = 16;
     constexpr int TT = NX * TLEN;                              // samples per stage
-    constexpr int kXStage = NX * kTileBytes, kYTile = 2 * NX * kTileBytes;
+    constexpr bool kBulkRows = PASS_B && NX == 2;              // see tma_cta (pfb_tma.cuh) and profiles/r03d_bulk_rows.txt
+    constexpr int kRowStride = out_row_stride(2 * NX);
+    constexpr int kXStage = NX * kTileBytes, kYTile = kBulkRows ? out_slot_bytes(2 * NX) : 2 * NX * kTileBytes;
     constexpr int S = 2 * ORDER;
     const int lane = threadIdx.x & 31, key = lane & 7;
     const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
@@ -133,6 +137,9 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
     }
     char *ybuf = ys + warp * kYTile;
     char *yrow = ybuf + lane * kRowBytes;
+    char *orow = ybuf + lane * kRowStride;                      // kBulkRows: this lane's linear row of 2 TT complex samples
+    char *grow = kBulkRows ? reinterpret_cast<char *>(p.y + ((size_t)q * (size_t)p.ldy2 + (size_t)j * (size_t)(2 * p.L)))
+                           : nullptr;
 
     long long t = t_first;
     for (; t < t_mine; ++t) {
@@ -148,11 +155,12 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
         const char *xrow = xs + s * kXStage + lane * kRowBytes;
         // every 128-byte output half is its own bulk group: before half k of this tile is overwritten only the
         // store of half k of the previous tile must have been read, the later halves may still be draining
+        if (kBulkRows) bulk_wait_read0();          // this lane's copy of the previous stage has left its row
 #pragma unroll
         for (int h = 0; h < NX; ++h) {
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
-                if (PASS_B) {
+                if (PASS_B && !kBulkRows) {
                     if (lane == 0) bulk_wait_read_upto(2 * NX - 1 - (2 * h + part));
                     __syncwarp();
                 }
@@ -163,18 +171,25 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
                     double yr, yi;
                     fos_sample<ORDER>(in.x, gain, cr, ci, zr, zi, yr, yi);
                     // complex sample 2 v of input half h -> output half 2 h + part, 16-byte chunk (2 v) % 8
-                    if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v) & 7) ^ key) << 4)) = make_double2(yr, yi);
+                    // (kBulkRows: complex sample 16 h + 2 v of the lane's linear row)
+                    if (kBulkRows) *reinterpret_cast<double2 *>(orow + ((16 * h + 2 * v) << 4)) = make_double2(yr, yi);
+                    else if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v) & 7) ^ key) << 4)) = make_double2(yr, yi);
                     fos_sample<ORDER>(in.y, gain, cr, ci, zr, zi, yr, yi);
-                    if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v + 1) & 7) ^ key) << 4)) = make_double2(yr, yi);
+                    if (kBulkRows) *reinterpret_cast<double2 *>(orow + ((16 * h + 2 * v + 1) << 4)) = make_double2(yr, yi);
+                    else if (PASS_B) *reinterpret_cast<double2 *>(yhalf + ((((2 * v + 1) & 7) ^ key) << 4)) = make_double2(yr, yi);
                 }
             }
         }
         if (PASS_B) fence_proxy_async();
         else asm volatile("fence.acq_rel.cta;\n" ::: "memory");   // pre-pass: see stage_release_after_reads (pfb_tma.cuh)
+        if (kBulkRows) {
+            if (row_ok) bulk_store_1d(grow + (size_t)t * (2 * NX * kRowBytes), orow, 2 * NX * kRowBytes);
+            bulk_commit();
+        }
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[s]);
-            if (PASS_B) {
+            if (PASS_B && !kBulkRows) {
 #pragma unroll
                 for (int h = 0; h < 2 * NX; ++h) {
                     tma_store_4d(&ymap, ybuf + h * kTileBytes, (int)(2 * t * TT + h * TLEN), p.JR * w, band, p.CH * cb);
@@ -184,7 +199,7 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
         }
     }
     if (PASS_B) {
-        if (lane == 0) bulk_wait0();
+        if (kBulkRows || lane == 0) bulk_wait0();
         if (row_ok && j == p.J - 1) {
             double *st = p.states + (size_t)q * S;
 #pragma unroll
