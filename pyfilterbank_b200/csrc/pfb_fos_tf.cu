@@ -354,7 +354,7 @@ static int run_fos_tma_nx(const FosTmaParams &p, const FosCoef &tab, const TmaPa
     auto ka = fos_tma_kernel<ORDER, false, NX>;
     auto kb = fos_tma_kernel<ORDER, true, NX>;
     const int smem_a = kFosStages * NX * kTileBytes + 2 * kFosStages * 8;
-    const int smem_b = kFosStages * NX * kTileBytes + p.nb * (NX == 2 ? out_slot_bytes(2 * NX) : 2 * NX * kTileBytes) + 2 * kFosStages * 8;
+    const int smem_b = kFosStages * NX * kTileBytes + p.nb * out_slot_bytes(2 * NX) + 2 * kFosStages * 8;
     cudaError_t e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     if (e != cudaSuccess) return (int)e;

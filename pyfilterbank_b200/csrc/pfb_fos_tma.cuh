@@ -58,7 +58,9 @@ fos_tma_kernel(const __grid_constant__ FosTmaParams p, const __grid_constant__ F
     extern __shared__ __align__(1024) char smem[];
     constexpr int TLEN = 16;
     constexpr int TT = NX * TLEN;                              // samples per stage
-    constexpr bool kBulkRows = PASS_B && NX == 2;              // see tma_cta (pfb_tma.cuh) and profiles/r03d_bulk_rows.txt
+    // every lane copies its own row fragment (256 NX bytes of complex samples) with a one-dimensional bulk copy: see
+    // tma_cta (pfb_tma.cuh); cfg 4: 18.1-18.9 -> 15.9-16.9 ms (NX = 2), 19.4-21.2 -> 17.2 ms (NX = 1), profiles/r03d_bulk_rows.txt
+    constexpr bool kBulkRows = PASS_B;
     constexpr int kRowStride = out_row_stride(2 * NX);
     constexpr int kXStage = NX * kTileBytes, kYTile = kBulkRows ? out_slot_bytes(2 * NX) : 2 * NX * kTileBytes;
     constexpr int S = 2 * ORDER;
