@@ -60,6 +60,30 @@ __global__ void __launch_bounds__(256) bulk1d_wr(double *y, long long L, long lo
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
 
+// The same store pattern with plain global stores issued COOPERATIVELY: per step the warp writes its 32 row fragments one
+// after the other, every instruction one contiguous piece of 512 bytes (32 lanes x 16 bytes) of ONE row -- no TMA.
+// CS: 0 default stores, 1 st.global.cs (streaming)
+template <int FRAG, int CS>
+__global__ void __launch_bounds__(256) coop_wr(double *y, long long L, long long n, int groups) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = (blockIdx.x / groups) * 8 + warp, w = blockIdx.x % groups;
+    char *base = reinterpret_cast<char *>(y + (size_t)q * n + (size_t)(32 * w) * L);     // row r: base + r * L * 8
+    const long long nt = L * 8 / FRAG;
+    const double v0 = 1.0 + lane, v1 = 2.0;
+    for (long long t = 0; t < nt; ++t) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            char *row = base + (size_t)r * L * 8 + t * FRAG;
+#pragma unroll
+            for (int c = 0; c < FRAG / 512; ++c) {
+                double *p = reinterpret_cast<double *>(row + c * 512 + lane * 16);
+                if (CS) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v0), "d"(v1) : "memory");
+                else asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v0), "d"(v1) : "memory");
+            }
+        }
+    }
+}
+
 // HINT: 1 evict_first, 2 evict_last, 3 evict_unchanged (createpolicy.fractional), BOXES boxes per step
 template <int BOXES, int HINT>
 __global__ void __launch_bounds__(256) tma_wr_hint(const __grid_constant__ CUtensorMap ymap, long long L, int groups, int) {
@@ -171,6 +195,19 @@ int main(int argc, char **argv) {
                    cudaGetErrorString(cudaGetLastError()));
         };
         run1d(bulk1d_wr<128>, 128); run1d(bulk1d_wr<256>, 256); run1d(bulk1d_wr<512>, 512); run1d(bulk1d_wr<1024>, 1024);
+        auto runc = [&](auto kern, const char *name) {
+            float best = 1e9;
+            for (int it = 0; it < 3; ++it) {
+                cudaEventRecord(e0);
+                kern<<<Q / 8 * groups, 256>>>(y, L, n, groups);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+            }
+            printf("cooperative global stores, %s  J=%3d: %7.3f ms  %.0f GB/s  (%s)\n", name, J, best, bytes / (best * 1e-3) / 1e9,
+                   cudaGetErrorString(cudaGetLastError()));
+        };
+        runc(coop_wr<512, 0>, "512-byte row pieces, st.global   "); runc(coop_wr<512, 1>, "512-byte row pieces, st.global.cs");
+        runc(coop_wr<1024, 1>, "1024-byte row pieces, st.global.cs");
         for (int vb : {16, 32}) {
             float best = 1e9;
             for (int it = 0; it < 3; ++it) {
