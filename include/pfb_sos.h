@@ -52,6 +52,12 @@ typedef enum pfb_status {
 #define PFB_EXACT 0x10      /* no FMA contraction, the reference's operation order: with PFB_MODE_SEQ the
                                result is bit-identical to sosfilt.c */
 #define PFB_ARITH_F64 0x20  /* float32 signals, float64 coefficients/states/arithmetic */
+#define PFB_ARITH_AUTO 0x200 /* with PFB_ARITH_F64 (float32 signals, float64 states): the arithmetic is chosen PER BAND --
+                               float32 where a calibration run at bank level shows float32 arithmetic within 1e-5
+                               (relative L2) of float64, float64 elsewhere -- so every band stays within 1e-4 of the
+                               double result while the well-conditioned bands run at the float32 rate
+                               (pfb_bank_f32_bands() tells how many; time-chunked TMA kernels only, other paths
+                               compute everything in float64) */
 #define PFB_DECIMATE2 0x40  /* store only every second output sample: y rows hold (n - phase + 1) / 2 samples,
                                output i = filtered sample 2 i + phase (the anti-alias stage of the decimating
                                band path; banks with K in {1,2,3,4,6,8} only) */
@@ -254,6 +260,9 @@ PFB_API int pfb_design_butter_sos(int kind, int L, const double *v1, const doubl
  * numerator and denominator share a root).  a0 normalises the section as scipy does.  Synchronises the stream. */
 PFB_API int pfb_states_convert(double *states_dev, const double *sos, int64_t Q, int B, int K, int per_row, int to_df2t,
                                void *stream);
+
+/* number of bands PFB_ARITH_AUTO runs in float32 arithmetic (calibrated on first use; negative: error) */
+PFB_API int pfb_bank_f32_bands(pfb_bank *bank);
 
 PFB_API const char *pfb_version(void);
 

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("PFB_SOS_LIB") or os.path.join(_HERE, "libpfb_sos.so")
 
 PFB_F32, PFB_F64 = 0, 1
 MODE_AUTO, MODE_SEQ, MODE_SCAN = 0, 1, 2
-EXACT, ARITH_F64, DECIMATE2, DEC_PHASE1 = 0x10, 0x20, 0x40, 0x80
+EXACT, ARITH_F64, DECIMATE2, DEC_PHASE1, ARITH_AUTO = 0x10, 0x20, 0x40, 0x80, 0x200
 _MODES = {"auto": MODE_AUTO, "seq": MODE_SEQ, "scan": MODE_SCAN}
 
 
@@ -60,6 +60,8 @@ def lib():
         L.pfb_bank_timing_begin.restype = ci
         L.pfb_bank_timing_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
         L.pfb_bank_timing_end.restype = ci
+        L.pfb_bank_f32_bands.argtypes = [vp]
+        L.pfb_bank_f32_bands.restype = ci
         L.pfb_bank_set_warm_tol.argtypes = [vp, ctypes.c_double]
         L.pfb_bank_set_warm_tol.restype = ci
         L.pfb_fos_bank_c128.argtypes = [vp, i64, vp, i64, vp, ci, ci, vp, i64, ci, vp]
@@ -122,7 +124,9 @@ def flags_of(mode="auto", exact=False, arith64=False, decimate=None):
     f = _MODES[mode]
     if exact:
         f |= EXACT
-    if arith64:
+    if arith64 == "auto":             # float64 states, arithmetic chosen per band (PFB_ARITH_AUTO)
+        f |= ARITH_F64 | ARITH_AUTO
+    elif arith64:
         f |= ARITH_F64
     if decimate is not None:          # phase 0 / 1 of the decimate-by-2 store
         f |= DECIMATE2 | (DEC_PHASE1 if decimate else 0)
@@ -181,6 +185,13 @@ class Bank:
     def filter_host(self, dtype, x, ldx, y, ldy, states, n, C, flags=0):
         check(lib().pfb_bank_filter_host(self._h, dtype, x.ctypes.data, ldx, y.ctypes.data, ldy,
                                          states.ctypes.data, n, C, flags))
+
+    def f32_bands(self):
+        """number of bands that arith64='auto' runs in float32 arithmetic (calibrated by the library on first use)"""
+        n = lib().pfb_bank_f32_bands(self._h)
+        if n < 0:
+            check(n)
+        return n
 
     def set_warm_tol(self, tol):
         """Relative-L2 budget of the truncated pre-pass of the time-chunked kernel (0: exact)."""

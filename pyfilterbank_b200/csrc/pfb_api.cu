@@ -130,6 +130,13 @@ struct pfb_bank {
     // device staging buffers of pfb_bank_filter_host (two input and two output slots), kept between calls
     void *hx[2] = {nullptr, nullptr}, *hy[2] = {nullptr, nullptr};
     size_t hx_bytes = 0, hy_bytes = 0;
+    // PFB_ARITH_AUTO: per-band choice of arithmetic for float32 signals (calibrated once, ensure_auto_arith)
+    int auto_state = 0;                 // 0 not calibrated, 1 ready, -1 failed
+    int f32_bands = 0;
+    unsigned *f32mask_dev = nullptr;    // bit b: band b runs in float32 arithmetic
+    float *cf32_dev = nullptr;          // [B][K][5] plain coefficients as float
+    int ensure_auto_arith();
+    bool auto_now = false;              // the call in progress asked for PFB_ARITH_AUTO (set under `mu`)
     double *gains_dev[2] = {nullptr, nullptr};   // gain tables when no chunk tables are needed (single chunk)
     double *gains_only(int arith);
     // streams and events of the host-buffer entry points (pfb_bank_filter_host, pfb_bank_levels_host), created once
@@ -156,6 +163,77 @@ int pfb_bank::ensure_host_ctx() {
 
 // Gain tables of the normalised float64 arithmetic (single-sweep banks with well-scaled b0 only):
 // [rows][K][2] = (G_k, 1 / G_k), G_k = b0_0 ... b0_{k-1}.  Null: plain arithmetic.
+// PFB_ARITH_AUTO calibration: every band's cascade on 32768 samples of pseudo-random noise, once in the float32 arithmetic
+// of the kernels (Biquad<float, false>::step: fused multiply-adds, float coefficients and states) and once in float64;
+// a band runs in float32 where the two agree to 1e-5 relative L2 -- a factor 10 under the 1e-4 the float32 path has to
+// meet against the double result.  Rounding noise of a stable section is stationary, so the ratio does not grow with
+// the signal length; the low bands fail it by orders of magnitude (poles at radius 0.9999, angle 1e-3).
+int pfb_bank::ensure_auto_arith() {
+    if (auto_state != 0) return auto_state > 0 ? PFB_OK : fail(PFB_ERR_CUDA, "PFB_ARITH_AUTO: calibration tables unavailable");
+    if (per_channel) {
+        auto_state = -1;
+        return fail(PFB_ERR_INVALID, "PFB_ARITH_AUTO needs a bank with shared coefficients");
+    }
+    const int n = 32768;
+    std::vector<double> x(n);
+    unsigned long long lcg = 0x9E3779B97F4A7C15ULL;
+    for (int i = 0; i < n; ++i) {   // sum of four uniforms: close enough to Gaussian noise for a rounding-error estimate
+        double v = 0;
+        for (int r = 0; r < 4; ++r) {
+            lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+            v += (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+        }
+        x[i] = 0.1 * v;
+    }
+    std::vector<unsigned> mask((B + 31) / 32, 0u);
+    std::vector<float> cf((size_t)B * K * 5);
+    f32_bands = 0;
+    for (int b = 0; b < B; ++b) {
+        const double *c = &coef_host[(size_t)b * K * 5];
+        for (int i = 0; i < K * 5; ++i) cf[(size_t)b * K * 5 + i] = (float)c[i];
+        std::vector<double> w64(2 * K, 0.0);
+        std::vector<float> w32(2 * K, 0.0f);
+        double num = 0, den = 0;
+        for (int i = 0; i < n; ++i) {
+            double s64 = x[i];
+            float s32 = (float)x[i];
+            for (int k = 0; k < K; ++k) {
+                const double *q = c + 5 * k;
+                const double w0 = s64 - q[3] * w64[2 * k] - q[4] * w64[2 * k + 1];
+                s64 = q[0] * w0 + q[1] * w64[2 * k] + q[2] * w64[2 * k + 1];
+                w64[2 * k + 1] = w64[2 * k];
+                w64[2 * k] = w0;
+                const float *qf = &cf[((size_t)b * K + k) * 5];
+                const float t = std::fmaf(-qf[4], w32[2 * k + 1], s32);
+                const float u = std::fmaf(qf[1], w32[2 * k], qf[2] * w32[2 * k + 1]);
+                const float w0f = std::fmaf(-qf[3], w32[2 * k], t);
+                s32 = std::fmaf(qf[0], w0f, u);
+                w32[2 * k + 1] = w32[2 * k];
+                w32[2 * k] = w0f;
+            }
+            const double d = (double)s32 - s64;
+            num += d * d;
+            den += s64 * s64;
+        }
+        const bool ok = std::isfinite(num) && den > 0 && std::sqrt(num / den) <= 1e-5;
+        if (ok) {
+            mask[b >> 5] |= 1u << (b & 31);
+            ++f32_bands;
+        }
+    }
+    cudaError_t e = counted_malloc(&f32mask_dev, mask.size() * sizeof(unsigned));
+    if (e == cudaSuccess) e = counted_malloc(&cf32_dev, cf.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(f32mask_dev, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(cf32_dev, cf.data(), cf.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);   // pageable copies may return before the DMA has landed
+    if (e != cudaSuccess) {
+        auto_state = -1;
+        return fail(PFB_ERR_CUDA, "PFB_ARITH_AUTO: %s", cudaGetErrorString(e));
+    }
+    auto_state = 1;
+    return PFB_OK;
+}
+
 double *pfb_bank::gains_only(int arith) {
     if (arith != PFB_F64 || sweeps.size() != 1 || getenv("PFB_NO_SCALED")) return nullptr;
     if (gains_dev[0]) return gains_dev[0];
@@ -605,6 +683,10 @@ static int tma_run(pfb_bank *b, int dtype, bool arith64, const void *x, long lon
     tp.zs = ws.first;
     tp.states = states;
     tp.y = y, tp.ldy = ldy, tp.By = By;
+    if (b->auto_now && b->auto_state == 1 && dtype == PFB_F32 && arith64 && !weighted && !dec && !levels) {
+        tp.f32mask = b->f32mask_dev;
+        tp.cf32 = b->cf32_dev;
+    }
     tp.L = Lt;
     tp.Q = Q, tp.B = b->B, tp.C = C, tp.J = J, tp.nb = nb, tp.G = G;
     tp.JR = JR, tp.CH = CH, tp.NW = J / JR, tp.CB = (C + CH - 1) / CH;
@@ -739,6 +821,8 @@ void pfb_bank_destroy(pfb_bank *b) {
     for (cudaEvent_t e : b->tevents) cudaEventDestroy(e);
     cudaFree(b->gains_dev[0]);
     cudaFree(b->gains_dev[1]);
+    cudaFree(b->f32mask_dev);
+    cudaFree(b->cf32_dev);
     for (int i = 0; i < 2; ++i) {
         cudaFree(b->hx[i]);
         cudaFree(b->hy[i]);
@@ -812,6 +896,16 @@ int pfb_bank_timing_end(pfb_bank *b, double *ms, int *calls) {
     return PFB_OK;
 }
 
+static int check_device(const pfb_bank *b, const char *who);
+
+int pfb_bank_f32_bands(pfb_bank *b) {
+    if (!b) return fail(PFB_ERR_INVALID, "pfb_bank_f32_bands: null bank");
+    std::lock_guard<std::mutex> lock(b->mu);
+    if (int rc = check_device(b, "pfb_bank_f32_bands")) return rc;
+    if (int rc = b->ensure_auto_arith()) return rc;
+    return b->f32_bands;
+}
+
 int pfb_bank_last_launch(const pfb_bank *b, pfb_launch_info *info) {
     if (!b || !info) return fail(PFB_ERR_INVALID, "pfb_bank_last_launch: null argument");
     *info = b->last;
@@ -864,8 +958,14 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
     const long long Qll = (long long)C * b->B;
     if (Qll > 0x7fffffffLL) return fail(PFB_ERR_INVALID, "pfb_bank_filter: C*B = %lld exceeds 2^31-1", Qll);
     const bool exact = (flags & PFB_EXACT) != 0;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;       // per-band arithmetic lives on the float64-state path
     const bool arith64 = dtype == PFB_F64 || (flags & PFB_ARITH_F64);
-    if (dtype == PFB_F64 && (flags & PFB_ARITH_F64)) flags &= ~PFB_ARITH_F64;
+    if (dtype == PFB_F64 && (flags & PFB_ARITH_F64)) flags &= ~(PFB_ARITH_F64 | PFB_ARITH_AUTO);
+    b->auto_now = false;
+    if ((flags & PFB_ARITH_AUTO) && !exact && !b->per_channel) {
+        if (int rca = b->ensure_auto_arith()) return rca;
+        b->auto_now = true;
+    }
     if (exact && (flags & PFB_ARITH_F64))
         return fail(PFB_ERR_INVALID, "pfb_bank_filter: PFB_EXACT and PFB_ARITH_F64 are mutually exclusive");
     int mode = flags & PFB_MODE_MASK;
@@ -928,6 +1028,16 @@ static int bank_filter_locked(pfb_bank *b, int dtype, const void *x, int64_t ldx
         bool wide = b->K <= 4 && b->B >= 9 && J >= 32 && (long long)C * Gw * 4 >= 2LL * b->sm_count;
         wide = env_int("PFB_TMA_WIDE", wide ? 1 : 0) != 0;
         if (ex) wide = false;               // the fused stages live in the 256-byte-fragment kernel
+        // Per-band arithmetic (PFB_ARITH_AUTO): the 256-byte-fragment kernel with 11 bands per CTA, two CTAs per SM --
+        // the float64 warps of two CTAs keep the FP64 pipe busier than one CTA's share of them does (cfg 2 output pass
+        // 6.28 ms against 6.88 ms on the wide kernel and 7.39 ms with 7 bands per CTA, profiles/r04b_auto_arith_variants.txt)
+        if (b->auto_now && dtype == PFB_F32 && arith64 && !ex && b->K <= 4) {
+            wide = env_int("PFB_TMA_WIDE", 0) != 0;
+            if (!wide) {
+                tma_bands(b, &nb, &G, true);
+                J = tma_pick_J(b, n, C, tt, arith64, G, 1 << 30, false);
+            }
+        }
         if (ex && ex->wnz) {
             J = 1;                          // the weighting recurrence is sequential in time: rows are whole channels
             // Bands per CTA (sos_tma_weighted_kernel: 9 band warps on three SM sub-partitions, the weighting warp alone

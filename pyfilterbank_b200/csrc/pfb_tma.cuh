@@ -76,6 +76,10 @@ struct TmaParams {
     void *y;
     long long ldy;
     int By;
+    // PFB_ARITH_AUTO (float32 signals, float64 states): bands whose bit is set in f32mask run the output pass in float32
+    // arithmetic with the plain coefficients cf32 [B][K][5] (float); null: every band in the kernel's arithmetic type
+    const unsigned *f32mask;
+    const float *cf32;
     // PFB_WARP_PROF builds only: clocks per warp role, [warp index][0 wait for input, 1 arithmetic, 2 wait for the
     // output buffer, 3 total, 4 proxy fence + warp sync, 5 barrier arrive + store issue], summed over CTAs (lane 0's clock64)
     unsigned long long *prof;
@@ -496,8 +500,15 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     const int cg = cta / p.NW;
     const int nbw = PASS_B ? p.nb : p.nb_a, G = PASS_B ? p.G : p.G_a;
     const int g = cg % G, cb = ch0 + cg / G;
-    const int b0 = g * nbw;
-    const int nb_here = min(nbw, p.B - b0);
+    // Band -> (CTA, warp slot).  Contiguous groups (slot s of group g filters band g * nbw + s) everywhere but in the
+    // output pass with a per-band choice of arithmetic (kMixed with p.f32mask): there group g takes the bands g, g + G,
+    // g + 2 G, .. so that every CTA holds its share of the float64 bands (the low ones) -- the FP64 pipe of each SM is
+    // then loaded evenly instead of one CTA in G running all-float64.  The chunk states in zs are indexed by band, so
+    // the pre-pass keeps its own (contiguous, heavy-first) grouping.
+    constexpr bool kMixed = STORE_Y && !WEIGHT && !DEC && sizeof(T) == 4 && sizeof(A) == 8;
+    const int bstep = kMixed && p.f32mask != nullptr ? G : 1;
+    const int b0 = bstep > 1 ? g : g * nbw;
+    const int nb_here = bstep > 1 ? (p.B - g + G - 1) / G : min(nbw, p.B - b0);
 
     char *xs = smem;                                          // [stages][2][tile]
     // Output pass: the lanes copy their own row fragments (NH * 128 contiguous bytes each) to global memory with
@@ -583,7 +594,7 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     if (slot >= nb_here) return;
 
     // ---------------- consumers: one band per warp, one (channel, chunk) row per lane ----------------
-    const int band = b0 + slot;
+    const int band = b0 + slot * bstep;
     const int chn = p.CH * cb + lane / p.JR;
     const bool row_ok = chn < p.C;                // channel blocks may be ragged: TMA clips the tile, lanes idle
     const int q = (row_ok ? chn : 0) * p.B + band;
@@ -593,13 +604,27 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
     // a second, independently reduced copy of the band index that is used for nothing but the
     // coefficient table, so its users stay on the uniform datapath
     const int warp_u = __reduce_min_sync(0xffffffffu, (int)(threadIdx.x >> 5));
-    const int band_u = b0 + (WEIGHT ? warp_u - (warp_u >> 2) : warp_u);
+    const int band_u = b0 + (WEIGHT ? warp_u - (warp_u >> 2) : warp_u) * bstep;
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int i = 0; i < 5; ++i) c[k][i] = tab.c[band_u * K + k][i];
     A *zs = reinterpret_cast<A *>(p.zs) + ((size_t)q * p.J + j) * S;
     const double *gain = SCALED ? p.gains + (size_t)band * K * 2 : nullptr;
+    // per-band choice of arithmetic (float32 signals with float64 states, output pass): warp-uniform
+    bool use_f32 = false;
+    float cf[K][5], wf[K][2];
+    if (kMixed && p.f32mask != nullptr) use_f32 = ((p.f32mask[band >> 5] >> (band & 31)) & 1u) != 0;
+    if (kMixed && use_f32) {
+        const A *z0 = p.J == 1 ? cascade_states<A>(p, row_ok ? chn : 0, band) : zs;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) cf[k][i] = __ldg(p.cf32 + ((size_t)band * K + k) * 5 + i);
+            wf[k][0] = (float)z0[2 * k];
+            wf[k][1] = (float)z0[2 * k + 1];
+        }
+    }
     if (PASS_B) {
         // a single chunk per cascade starts from the carried-in states themselves (no pre-pass, no carry kernel)
         const A *z0 = p.J == 1 ? cascade_states<A>(p, row_ok ? chn : 0, band) : zs;
@@ -734,7 +759,12 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
                     __syncwarp();
                 }
                 PROF_LAP(2);
-                filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
+                if constexpr (kMixed) {
+                    if (use_f32) filter_half<float, float, K, 1, false>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, cf, wf);
+                    else filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
+                } else {
+                    filter_half<T, A, K, 1, SCALED>(xrow + h * kTileBytes, yrow + yb + h * kTileBytes, key, c, wst);
+                }
                 PROF_LAP(1);
             }
             fence_proxy_async();
@@ -779,8 +809,8 @@ __device__ __forceinline__ void tma_cta(const TmaParams &p, const CoefTable<A> &
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const A gk = SCALED ? (A)gain[2 * k] : A(1);
-                st[2 * k] = wst[k][0] * gk;
-                st[2 * k + 1] = wst[k][1] * gk;
+                st[2 * k] = kMixed && use_f32 ? (A)wf[k][0] : wst[k][0] * gk;
+                st[2 * k + 1] = kMixed && use_f32 ? (A)wf[k][1] : wst[k][1] * gk;
             }
         }
     } else if (row_ok) {

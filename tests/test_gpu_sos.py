@@ -277,6 +277,60 @@ def test_tma_path_f32(pfb, oracle):
         assert rel_l2(y2[:, b], yd[:, b]) <= max(10 * ref_err, 1e-5), (b, ref_err, rel_l2(y2[:, b], yd[:, b]))
 
 
+@pytest.mark.parametrize("J,wide", [(0, None), (1, 0), (4, 0), (32, 0), (64, 0), (64, 1), (128, 1)])
+def test_f32_auto_arithmetic(pfb, oracle, J, wide, monkeypatch):
+    """PFB_ARITH_AUTO (arith64='auto'): float32 signals, float64 states, arithmetic chosen per band -- float32 where the
+    library's calibration finds it within 1e-5 of float64, float64 elsewhere.  Every band must stay within the
+    north-star tolerance of 1e-4 against the double oracle (sosfilt.c:31-54 on the float32-rounded input), the
+    carried states must continue a block-wise run, and some but not all bands of the 1/3-octave bank run in float32.
+    Covers the 256-byte-fragment kernel, the wide one (strided band groups) and ragged channel blocks."""
+    if J:
+        monkeypatch.setenv("PFB_TMA_J", str(J))
+    if wide is not None:
+        monkeypatch.setenv("PFB_TMA_WIDE", str(wide))
+    rng = np.random.default_rng(400 + J)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    bank = pfb.Bank(sos)
+    nf = bank.f32_bands()
+    assert 8 <= nf < B, nf
+    for C, n in ((3, 131072), (37, 65536)):
+        x = rng.standard_normal((C, n)).astype(np.float32)
+        st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+        yd, sd = oracle.sos_bank(x.astype(np.float64), sos, st0)
+        xt = torch.from_numpy(x).cuda()
+        y1, s1 = pfb.bank_filter(bank, xt, torch.from_numpy(st0.copy()).cuda(), arith64="auto")
+        assert bank.last_launch()["aligned"] in (2, 3)
+        assert y1.dtype == torch.float32 and s1.dtype == torch.float64
+        y1 = y1.cpu().numpy()
+        errs = np.array([rel_l2(y1[:, b], yd[:, b]) for b in range(B)])
+        assert errs.max() <= 1e-4, (C, n, int(errs.argmax()), errs.max())
+        # the float64 bands are as accurate as PFB_ARITH_F64 alone: only float32 output rounding is left
+        assert np.sort(errs)[: B - nf].max() <= 1e-6, np.sort(errs)
+        # block-wise == one shot within the same tolerance (states carried in float64)
+        h = n // 2
+        ya, sa = pfb.bank_filter(bank, xt[:, :h].contiguous(), torch.from_numpy(st0.copy()).cuda(), arith64="auto")
+        yb, sb = pfb.bank_filter(bank, xt[:, h:].contiguous(), sa, arith64="auto")
+        y2 = torch.cat([ya, yb], dim=2).cpu().numpy()
+        assert max(rel_l2(y2[:, b], yd[:, b]) for b in range(B)) <= 1e-4
+        assert rel_l2(sb.cpu().numpy(), sd) <= 1e-3
+
+
+def test_f32_auto_needs_shared_coefficients_and_falls_back(pfb, oracle):
+    """Outside the time-chunked TMA kernels (sequential mode, short signals) PFB_ARITH_AUTO computes everything in
+    float64; on float64 signals the flag is ignored."""
+    rng = np.random.default_rng(5)
+    sos = _bank48()
+    B = sos.shape[0]
+    x = rng.standard_normal((2, 4096)).astype(np.float32)
+    yd, _ = oracle.sos_bank(x.astype(np.float64), sos)
+    bank = pfb.Bank(sos)
+    y1, _ = pfb.bank_filter(bank, torch.from_numpy(x).cuda(), mode="seq", arith64="auto")
+    assert max(rel_l2(y1.cpu().numpy()[:, b], yd[:, b]) for b in range(B)) <= 1e-6
+    y2, _ = pfb.bank_filter(bank, torch.from_numpy(x.astype(np.float64)).cuda(), arith64="auto")
+    assert max(rel_l2(y2.cpu().numpy()[:, b], yd[:, b]) for b in range(B)) <= 1e-9
+
+
 @pytest.mark.parametrize("J", [1, 2, 4, 8, 16, 32, 64])
 def test_tma_tile_shapes(pfb, oracle, J, monkeypatch):
     """Tile rows of the TMA kernels are (channel, chunk) pairs: J chunks per cascade, 32 / min(J, 32)
