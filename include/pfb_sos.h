@@ -196,8 +196,12 @@ PFB_API int pfb_bank_filter_weighted(pfb_bank *bank, int dtype, const void *x, i
 
 /* Decimating band path (opt-in; the reference has no resampling): stage m = 0 .. nstages - 1
  * runs at fs / 2^m; the stage m + 1 signal is the stage m signal through the anti-alias cascade `aa_sos`, every
- * second sample kept.  One call filters all stages: per stage ONE pass over the stage signal produces the stage's
- * band signals and (as one more band warp with a decimating store) the next stage's signal.
+ * second sample kept.  One call filters all stages.  Default schedule ("split"): the anti-alias chain (one cascade per
+ * channel and stage, stored decimated) runs on a stream of its own, stage 0's bands on the caller's stream, the bands
+ * of stage m >= 1 on stream m as soon as signal m exists, and the caller's stream continues when all of them have
+ * finished -- the small stages overlap each other and stage 0.  PFB_DEC_SPLIT=0 (environment) or PFB_EXACT: stage by
+ * stage, per stage ONE pass over the stage signal produces the stage's band signals and (as one more band warp with a
+ * decimating store) the next stage's signal.  Either way a band signal is written once, at its own rate.
  *   bands_per_stage[m], sos_per_stage[m] : HOST [bands][K][6] (null for a stage without bands)
  *   aa_sos : HOST [Kaa][6]                                                                                   */
 typedef struct pfb_decbank pfb_decbank;
@@ -207,7 +211,8 @@ PFB_API void pfb_decbank_destroy(pfb_decbank *dec);
 /* x DEVICE [C][ldx] float64, n samples; y[m] DEVICE [C][bands m][ldy[m]] receives n_m samples per row with n_0 = n,
  * n_{m+1} = (n_m - phase_m + 1) / 2; band_states[m] DEVICE [C][bands m][K][2]; aa_states DEVICE
  * [nstages - 1][C][Kp][2] (Kp from pfb_decbank_info: the anti-alias cascade padded with pass-through sections);
- * phases HOST [nstages - 1] decimator phases, in/out.  flags: mode / PFB_EXACT.  Asynchronous on `stream`. */
+ * phases HOST [nstages - 1] decimator phases, in/out.  flags: mode / PFB_EXACT.  Asynchronous: later work on `stream`
+ * is ordered behind all of it; the buffers must not be touched from other streams before. */
 PFB_API int pfb_decbank_filter(pfb_decbank *dec, const double *x, int64_t ldx, void *const *y, const int64_t *ldy,
                                void *const *band_states, double *aa_states, int *phases, int64_t n, int C, int flags,
                                void *stream);

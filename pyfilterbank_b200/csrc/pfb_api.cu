@@ -58,6 +58,7 @@ struct Tables {          // device tables of one (arithmetic type, chunk length)
     double *H = nullptr;      // chunk-impulse-response tables of the GEMM-form pre-pass (pfb_tma.cuh), or null
     long long *Hoff = nullptr;
     size_t bytes = 0;         // device bytes held (cache accounting)
+    mutable unsigned long long last_use = 0;   // cache clock of the last call that used the set (eviction order)
 };
 
 void free_tables(Tables &t) {
@@ -137,6 +138,9 @@ struct pfb_bank {
     float *cf32_dev = nullptr;          // [B][K][5] plain coefficients as float
     int ensure_auto_arith();
     bool auto_now = false;              // the call in progress asked for PFB_ARITH_AUTO (set under `mu`)
+    unsigned long long table_clock = 0; // ensure_tables: use counter of the table cache
+    double slot_share = 1.0;            // share of the machine the chunk-count model may assume (stages that run side by side)
+    int force_J = 0;                    // chunk count imposed by the owner of the bank (0: cost model)
     double *gains_dev[2] = {nullptr, nullptr};   // gain tables when no chunk tables are needed (single chunk)
     double *gains_only(int arith);
     // streams and events of the host-buffer entry points (pfb_bank_filter_host, pfb_bank_levels_host), created once
@@ -405,19 +409,32 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
     auto key = std::make_tuple(arith, L, tt);
     auto it = b->tables.find(key);
     if (it != b->tables.end()) {
+        it->second.last_use = ++b->table_clock;
         *out = &it->second;
         return PFB_OK;
     }
     size_t cached_bytes = 0;
     for (auto &kv : b->tables) cached_bytes += kv.second.bytes;
-    // bound the cache (block-wise callers with a fixed block length hit it; the segment loop of the band-level path
-    // and the host-streaming paths add a handful of chunk lengths each); nothing may still be using the old tables
-    if (b->tables.size() >= 96 || cached_bytes > (3ULL << 30)) {
+    // Bound the cache (block-wise callers with a fixed block length hit it; the segment loop of the band-level path
+    // and the host-streaming paths add a handful of chunk lengths each): over 96 sets or 8 GiB (PFB_TABLE_CACHE_MB) the
+    // least recently used sets go until half the budget is free -- not all of them: a process that alternates between a
+    // few shapes (bench.py: device-resident step, host-buffer step, band levels, float32 variants; up to 0.8 GB each)
+    // would otherwise rebuild its tables on the host on every call (measured: 18 -> 320 ms per band-level call).
+    // Nothing may still be using the evicted tables.
+    const size_t cap = (size_t)std::max(64, env_int("PFB_TABLE_CACHE_MB", 8192)) << 20;
+    if (b->tables.size() >= 96 || cached_bytes > cap) {
         PFB_CUDA(cudaDeviceSynchronize());
-        for (auto &kv : b->tables) free_tables(kv.second);
-        b->tables.clear();
+        while (!b->tables.empty() && (b->tables.size() >= 64 || cached_bytes > cap / 2)) {
+            auto victim = b->tables.begin();
+            for (auto jt = b->tables.begin(); jt != b->tables.end(); ++jt)
+                if (jt->second.last_use < victim->second.last_use) victim = jt;
+            cached_bytes -= std::min(cached_bytes, victim->second.bytes);
+            free_tables(victim->second);
+            b->tables.erase(victim);
+        }
     }
     Tables t;
+    t.last_use = ++b->table_clock;
     // on a CUDA error the partial allocations held in t are released before returning
 #define PFB_CUDA_T(call)                                                                         \
     do {                                                                                         \
@@ -602,13 +619,14 @@ static int tma_pick_J(pfb_bank *b, long long n, int C, int tt, bool arith64, int
     int J = env_int("PFB_TMA_J", 0);
     if (env_int("PFB_TMA_GROUPS", 0) > 0) J = 32 * env_int("PFB_TMA_GROUPS", 0);
     if (J > 0 && J <= jmax) return J;
+    if (b->force_J > 0 && b->force_J <= jmax) return b->force_J;
     J = 1;
     if (b->wproxy.empty()) {   // decay length of every band (pre-pass window if chunks were unbounded)
         b->wproxy.resize(b->B);
         for (int r = 0; r < b->B; ++r)
             b->wproxy[r] = (double)warm_length(&b->sos[(size_t)r * b->K * 6], 0, b->K, 1LL << 20, arith64 ? 1e-11 : 1e-6);
     }
-    const double slots = (wide ? 1.0 : 2.0) * b->sm_count;   // resident output-pass CTAs
+    const double slots = (wide ? 1.0 : 2.0) * b->sm_count * b->slot_share;   // resident output-pass CTAs
     double best = 1e300;
     for (int cand = 0; cand < 13; ++cand) {
         const int j = cand < 5 ? (1 << cand) : 32 * (cand - 4);
@@ -1613,9 +1631,167 @@ struct pfb_decbank {
     pfb_bank *aa = nullptr;            // the anti-alias cascade alone (1 row, Kp sections)
     void *sig[2] = {nullptr, nullptr}; // stage signals (ping-pong): stage m reads sig[m & 1] (m > 0), writes sig[(m + 1) & 1]
     size_t sig_bytes[2] = {0, 0};
+    // split schedule (split_filter): every stage signal has its own buffer, the anti-alias chain its own stream, every
+    // stage's bands theirs
+    std::vector<void *> ssig;          // ssig[m]: signal of stage m (m >= 1)
+    std::vector<size_t> ssig_bytes;
+    cudaStream_t s_aa = nullptr;
+    std::vector<cudaStream_t> s_band;  // s_band[m], m >= 1 (stage 0 runs on the caller's stream)
+    cudaEvent_t ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_aa, ev_band;
+    int ensure_split(int C, long long n);
+    int split_filter(const double *x, int64_t ldx, void *const *y, const int64_t *ldy, void *const *band_states,
+                     double *aa_states, int *phases, int64_t n, int C, int flags, cudaStream_t stream);
     std::mutex mu;
-    int last_kernels = 0, last_fused = 0;
+    int last_kernels = 0, last_fused = 0, last_split = 0;
 };
+
+// ------------------------------------------------------------------------------------------------
+// Split schedule of the decimating band path.  The stage-by-stage schedule (below, pfb_decbank_filter) runs nine
+// dependent launch sets; stages 1 .. M hold few cascades each (13 of 119 bands per octave), so each of them fills the
+// machine badly and the next one cannot start before its last CTA has finished.  Only the anti-alias CHAIN is
+// sequential, though: stage m's bands need nothing but the stage signal m.  Here the chain (one cascade per channel and
+// stage, stored decimated by the same DEC kernels) runs on a high-priority stream of its own, stage 0's bands on the
+// caller's stream from the start, and the bands of stage m >= 1 on stream m as soon as signal m exists -- the small
+// stages overlap each other and the tail of stage 0.  Same kernels, same arithmetic, same stores: every band signal is
+// still written once at its own rate, and the anti-alias outputs only decimated.
+// ------------------------------------------------------------------------------------------------
+int pfb_decbank::ensure_split(int C, long long n) {
+    if (!s_aa) {
+        int lo = 0, hi = 0;
+        PFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PFB_CUDA(cudaStreamCreateWithPriority(&s_aa, cudaStreamNonBlocking, hi));
+        PFB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        s_band.assign(M + 1, nullptr);
+        ev_aa.assign(M + 1, nullptr);
+        ev_band.assign(M + 1, nullptr);
+        for (int m = 0; m <= M; ++m) {
+            if (m >= 1) PFB_CUDA(cudaStreamCreateWithPriority(&s_band[m], cudaStreamNonBlocking, hi));
+            PFB_CUDA(cudaEventCreateWithFlags(&ev_aa[m], cudaEventDisableTiming));
+            PFB_CUDA(cudaEventCreateWithFlags(&ev_band[m], cudaEventDisableTiming));
+        }
+        ssig.assign(M + 1, nullptr);
+        ssig_bytes.assign(M + 1, 0);
+    }
+    long long nm = n;
+    for (int m = 1; m <= M; ++m) {
+        nm = (nm + 1) / 2;
+        const long long pitch = (nm + 31) / 32 * 32;
+        const size_t need = (size_t)C * (size_t)pitch * sizeof(double);
+        if (ssig_bytes[m] < need) {
+            if (ssig[m]) {
+                PFB_CUDA(cudaDeviceSynchronize());
+                cudaFree(ssig[m]);
+                ssig[m] = nullptr;
+                ssig_bytes[m] = 0;
+            }
+            PFB_CUDA(counted_malloc(&ssig[m], need));
+            ssig_bytes[m] = need;
+        }
+    }
+    return PFB_OK;
+}
+
+int pfb_decbank::split_filter(const double *x, int64_t ldx, void *const *y, const int64_t *ldy, void *const *band_states,
+                              double *aa_states, int *phases, int64_t n, int C, int flags, cudaStream_t stream) {
+    if (int rc = ensure_split(C, n)) return rc;
+    last_kernels = last_fused = 0;
+    last_split = 1;
+    // PFB_DEC_SPLIT_TRACE=1: when each chain link and each stage finished, relative to the start of the call (stderr)
+    const bool trace = env_int("PFB_DEC_SPLIT_TRACE", 0) != 0;
+    std::vector<cudaEvent_t> tr_aa(M + 1, nullptr), tr_band(M + 1, nullptr);
+    cudaEvent_t tr0 = nullptr;
+    auto tr_rec = [&](cudaEvent_t &e, cudaStream_t st) {
+        if (!trace) return;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+    };
+    tr_rec(tr0, stream);
+    PFB_CUDA(cudaEventRecord(ev_start, stream));
+    PFB_CUDA(cudaStreamWaitEvent(s_aa, ev_start, 0));
+    // 1. the anti-alias chain: stage signal m -> m + 1, decimated stores only
+    std::vector<long long> len(M + 1), pitch(M + 1);
+    len[0] = n, pitch[0] = ldx;
+    {
+        const double *in = x;
+        long long nm = n;
+        for (int m = 0; m < M && nm > 0; ++m) {
+            const int ph = phases[m] & 1;
+            const long long n_next = (nm - ph + 1) / 2;
+            const long long pitch2 = ((nm + 1) / 2 + 31) / 32 * 32;
+            double *out2 = (double *)ssig[m + 1];
+            double *aast = aa_states + (size_t)m * C * Kp * 2;
+            long long done = 0;
+            {
+                FilterExtra ex;
+                ex.dec = true, ex.dec_phase = ph, ex.y2 = out2, ex.ldy2 = pitch2, ex.dec_states = aast;
+                std::lock_guard<std::mutex> block(aa->mu);
+                int rc = bank_filter_locked(aa, PFB_F64, in, pitch[m], nullptr, (nm + 31) / 32 * 32, (void *)aast, nm, C, flags,
+                                            (void *)s_aa, &ex);
+                if (rc < 0) return rc;
+                if (rc == PFB_OK && ex.n_done > 0) {
+                    done = ex.n_done;
+                    last_kernels += aa->last.kernels;
+                    ++last_fused;
+                }
+            }
+            if (done < nm) {
+                int rc = pfb_bank_filter(aa, PFB_F64, in + done, pitch[m], out2 + done / 2, pitch2, aast, nm - done, C,
+                                         flags | PFB_DECIMATE2 | (ph ? PFB_DEC_PHASE1 : 0), (void *)s_aa);
+                if (rc) return rc;
+                last_kernels += aa->last.kernels;
+            }
+            PFB_CUDA(cudaEventRecord(ev_aa[m], s_aa));
+            tr_rec(tr_aa[m], s_aa);
+            phases[m] = (int)((ph + nm) & 1);
+            in = out2;
+            len[m + 1] = n_next, pitch[m + 1] = pitch2;
+            nm = n_next;
+        }
+    }
+    // 2. the bands of every stage, each stage on its own stream behind the chain link that produces its signal
+    for (int m = 0; m <= M; ++m) {
+        if (nb[m] <= 0 || len[m] <= 0) continue;
+        if (m > 0 && len[m] > 0 && (!y[m] || !band_states[m] || ldy[m] < len[m]))
+            return fail(PFB_ERR_INVALID, "pfb_decbank_filter: stage %d needs an output of %lld samples per row", m, len[m]);
+        cudaStream_t st = m == 0 ? stream : s_band[m];
+        if (m > 0) PFB_CUDA(cudaStreamWaitEvent(st, ev_aa[m - 1], 0));
+        // The stages 1 .. M run side by side: their chunk counts are chosen as if each had an eighth of the machine
+        // (fewer chunks, less pre-pass work; measured 17.4-18.1 ms per 4 s block of cfg 3 against 18.3-18.8 with the
+        // whole machine assumed, profiles/r04f_dec_split_sweep.txt, r04i_dec_split_sweep.txt).  PFB_DEC_S0_J: chunks
+        // of stage 0 (experiments; 2 .. 16 are within the noise).
+        if (m > 0) bands[m]->slot_share = std::max(0.01, std::min(1.0, atof(getenv("PFB_DEC_SPLIT_SHARE") ? getenv("PFB_DEC_SPLIT_SHARE") : "0.125")));
+        if (m == 0) bands[m]->force_J = env_int("PFB_DEC_S0_J", 0);
+        const double *in = m == 0 ? x : (const double *)ssig[m];
+        int rc = pfb_bank_filter(bands[m], PFB_F64, in, pitch[m], y[m], ldy[m], band_states[m], len[m], C, flags, (void *)st);
+        if (rc) return rc;
+        last_kernels += bands[m]->last.kernels;
+        if (m > 0) PFB_CUDA(cudaEventRecord(ev_band[m], st));
+        tr_rec(tr_band[m], st);
+    }
+    // 3. join: the caller's stream continues when the chain and every stage have finished
+    if (M > 0) {
+        PFB_CUDA(cudaEventRecord(ev_aa[M], s_aa));
+        PFB_CUDA(cudaStreamWaitEvent(stream, ev_aa[M], 0));
+    }
+    for (int m = 1; m <= M; ++m)
+        if (nb[m] > 0 && len[m] > 0) PFB_CUDA(cudaStreamWaitEvent(stream, ev_band[m], 0));
+    if (trace) {
+        cudaStreamSynchronize(stream);
+        fprintf(stderr, "[dec split] finished at (ms after the start):");
+        for (int m = 0; m <= M; ++m) {
+            float a = -1.f, bnd = -1.f;
+            if (tr_aa[m]) cudaEventElapsedTime(&a, tr0, tr_aa[m]), cudaEventDestroy(tr_aa[m]);
+            if (tr_band[m]) cudaEventElapsedTime(&bnd, tr0, tr_band[m]), cudaEventDestroy(tr_band[m]);
+            fprintf(stderr, "  stage %d: chain %.2f bands %.2f (J=%d)", m, a, bnd,
+                    bands[m] ? bands[m]->last.warps_per_cascade * std::min<int>(32, std::max(1, (int)(len[m] / std::max<long long>(1, bands[m]->last.chunk)) )) : 0);
+        }
+        fprintf(stderr, "\n");
+        cudaEventDestroy(tr0);
+    }
+    g_status = PFB_OK;
+    return PFB_OK;
+}
 
 extern "C" {
 
@@ -1623,9 +1799,23 @@ void pfb_decbank_destroy(pfb_decbank *d) {
     if (!d) return;
     for (pfb_bank *b : d->fused) pfb_bank_destroy(b);
     for (pfb_bank *b : d->bands) pfb_bank_destroy(b);
+    if (d->s_aa) {
+        cudaStreamSynchronize(d->s_aa);
+        for (cudaStream_t st : d->s_band)
+            if (st) cudaStreamSynchronize(st);
+    }
     pfb_bank_destroy(d->aa);
     cudaFree(d->sig[0]);
     cudaFree(d->sig[1]);
+    for (void *q : d->ssig) cudaFree(q);
+    if (d->s_aa) cudaStreamDestroy(d->s_aa);
+    for (cudaStream_t st : d->s_band)
+        if (st) cudaStreamDestroy(st);
+    if (d->ev_start) cudaEventDestroy(d->ev_start);
+    for (cudaEvent_t e : d->ev_aa)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : d->ev_band)
+        if (e) cudaEventDestroy(e);
     delete d;
 }
 
@@ -1723,6 +1913,13 @@ int pfb_decbank_filter(pfb_decbank *d, const double *x, int64_t ldx, void *const
     }
     const bool exact = (flags & PFB_EXACT) != 0;
     const bool try_fused = d->fusable && !exact && !env_int("PFB_DEC_UNFUSED", 0);
+    d->last_split = 0;
+    if (try_fused && d->M > 0 && n > 0 && env_int("PFB_DEC_SPLIT", 1)) {
+        for (int m = 0; m <= d->M; ++m)
+            if (d->nb[m] > 0 && m == 0 && (!y[m] || !band_states[m] || ldy[m] < n))
+                return fail(PFB_ERR_INVALID, "pfb_decbank_filter: stage %d needs an output of %lld samples per row", m, (long long)n);
+        return d->split_filter(x, ldx, y, ldy, band_states, aa_states, phases, n, C, flags, stream);
+    }
     d->last_kernels = d->last_fused = 0;
     const double *in = x;
     long long ld_in = ldx, nm = n;
