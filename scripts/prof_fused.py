@@ -33,6 +33,14 @@ elif case == "tf":
     x = torch.randn(1024, 48000, device="cuda", dtype=torch.float64) * 0.1
     for _ in range(2):
         spl.tf_filter(b, a, x)
+elif case in ("cfg2auto", "cfg2fd"):      # float32 signals: per-band arithmetic / float64 arithmetic everywhere
+    g = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "designs.npz"))
+    s = g["third_48k_o4_sosmat"]; sos = np.ascontiguousarray(s.T).reshape(s.shape[1], -1, 6)
+    bank = p.get_bank(sos)
+    x = torch.randn(64, 1440000, device="cuda", dtype=torch.float32) * 0.1
+    y = torch.empty(64, 33, 1440000, device="cuda", dtype=torch.float32)
+    for _ in range(2):
+        p.bank_filter(bank, x, None, out=y, arith64="auto" if case == "cfg2auto" else True)
 elif case == "cfg3":
     ofb = p.FractionalOctaveFilterbank(sample_rate=48000, order=6, nth_oct=12.0, start_band=-67, end_band=51)
     x = (torch.randn(1024, 48000, device="cuda", dtype=torch.float64) * 0.1).t()
