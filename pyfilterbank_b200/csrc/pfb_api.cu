@@ -1644,6 +1644,7 @@ struct pfb_decbank {
                      double *aa_states, int *phases, int64_t n, int C, int flags, cudaStream_t stream);
     std::mutex mu;
     int last_kernels = 0, last_fused = 0, last_split = 0;
+    long long split_calls = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1709,6 +1710,9 @@ int pfb_decbank::split_filter(const double *x, int64_t ldx, void *const *y, cons
     tr_rec(tr0, stream);
     PFB_CUDA(cudaEventRecord(ev_start, stream));
     PFB_CUDA(cudaStreamWaitEvent(s_aa, ev_start, 0));
+    // a previous call (possibly issued from another stream) may still be reading the stage signals this one overwrites
+    if (split_calls++ > 0)
+        for (int m = 1; m <= M; ++m) PFB_CUDA(cudaStreamWaitEvent(s_aa, ev_band[m], 0));
     // 1. the anti-alias chain: stage signal m -> m + 1, decimated stores only
     std::vector<long long> len(M + 1), pitch(M + 1);
     len[0] = n, pitch[0] = ldx;
@@ -1751,7 +1755,10 @@ int pfb_decbank::split_filter(const double *x, int64_t ldx, void *const *y, cons
     }
     // 2. the bands of every stage, each stage on its own stream behind the chain link that produces its signal
     for (int m = 0; m <= M; ++m) {
-        if (nb[m] <= 0 || len[m] <= 0) continue;
+        if (nb[m] <= 0 || len[m] <= 0) {
+            if (m > 0) PFB_CUDA(cudaEventRecord(ev_band[m], s_band[m]));
+            continue;
+        }
         if (m > 0 && len[m] > 0 && (!y[m] || !band_states[m] || ldy[m] < len[m]))
             return fail(PFB_ERR_INVALID, "pfb_decbank_filter: stage %d needs an output of %lld samples per row", m, len[m]);
         cudaStream_t st = m == 0 ? stream : s_band[m];
