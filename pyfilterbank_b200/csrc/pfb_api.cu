@@ -1203,6 +1203,7 @@ int pfb_bank_levels_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, dou
     if (n <= 0 || C <= 0 || ldx < n || block_len <= 0 || n % block_len != 0 || ld_levels < n / block_len)
         return fail(PFB_ERR_INVALID, "pfb_bank_levels_host: bad sizes");
     const size_t esz = dtype == PFB_F64 ? 8 : 4;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;   // per-band arithmetic implies float64 states
     const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
     const int B = b->B;
     const long long nblocks = n / block_len;
@@ -1272,6 +1273,7 @@ int pfb_bank_levels_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, dou
 static int filter_host_by_channels(pfb_bank *b, int dtype, const void *x, int64_t ldx, void *y, int64_t ldy,
                                    void *states, int64_t n, int C, int flags, int Cg) {
     const size_t esz = dtype == PFB_F64 ? 8 : 4;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;   // per-band arithmetic implies float64 states
     const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
     const int B = b->B;
     const long long pitch = (n + 31) / 32 * 32;
@@ -1355,6 +1357,7 @@ static int levels_impl(pfb_bank *b, int dtype, const void *x, int64_t ldx, doubl
     if (dtype != PFB_F32 && dtype != PFB_F64) return fail(PFB_ERR_INVALID, "pfb_bank_levels: bad dtype %d", dtype);
     const int esz = dtype == PFB_F64 ? 8 : 4;
     const int tt = 2 * pfb::kRowBytes / esz;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;
     const bool arith64 = dtype == PFB_F64 || (flags & PFB_ARITH_F64);
     if (n <= 0 || C <= 0 || ldx < n || block_len <= 0 || n % block_len != 0 || block_len % tt != 0 ||
         ld_levels < n / block_len)
@@ -1459,6 +1462,7 @@ int pfb_bank_filter_host(pfb_bank *b, int dtype, const void *x, int64_t ldx, voi
     std::lock_guard<std::mutex> host_lock(b->host_mu);
     if (int rc0 = check_device(b, "pfb_bank_filter_host")) return rc0;
     const size_t esz = dtype == PFB_F64 ? 8 : 4;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;   // per-band arithmetic implies float64 states
     const size_t ssz = (dtype == PFB_F64 || (flags & PFB_ARITH_F64)) ? 8 : 4;
     const long long Q = (long long)C * b->B;
     const size_t nstate = (size_t)Q * b->K * 2;
@@ -2040,6 +2044,7 @@ int pfb_stream_create(pfb_stream **out, pfb_bank *bank, int dtype, int C, int64_
     pfb_stream *s = new pfb_stream;
     s->bank = bank;
     s->device = bank->device;
+    if (flags & PFB_ARITH_AUTO) flags |= PFB_ARITH_F64;   // per-band arithmetic implies float64 states
     s->dtype = dtype, s->C = C, s->flags = flags;
     s->max_block = max_block;
     s->pitch = (max_block + 31) / 32 * 32;

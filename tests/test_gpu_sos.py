@@ -385,6 +385,25 @@ def test_bank_filter_host_streaming(pfb, oracle, block_mb, monkeypatch):
     assert np.array_equal(ye, y0) and np.array_equal(st, s0)
 
 
+def test_f32_auto_host_buffers_flag_alone(pfb, oracle):
+    """PFB_ARITH_AUTO without the PFB_ARITH_F64 bit through the host-buffer entry point: the library treats the states
+    as float64 everywhere (a float32 reading of the state array would be memory corruption), results within 1e-4."""
+    from pyfilterbank_b200 import _lib
+    rng = np.random.default_rng(77)
+    sos = _bank48()
+    B, K = sos.shape[:2]
+    C, n = 3, 96000
+    x = rng.standard_normal((C, n)).astype(np.float32)
+    st0 = 0.01 * rng.standard_normal((C, B, K, 2))
+    yd, sd = oracle.sos_bank(x.astype(np.float64), sos, st0)
+    bank = pfb.Bank(sos)
+    y = np.empty((C, B, n), dtype=np.float32)
+    st = st0.copy()
+    bank.filter_host(_lib.PFB_F32, x, n, y, n, st, n, C, _lib.ARITH_AUTO)
+    assert max(rel_l2(y[:, b], yd[:, b]) for b in range(B)) <= 1e-4
+    assert rel_l2(st, sd) <= 1e-3
+
+
 def test_full_size_cfg2_properties(pfb, oracle):
     """BASELINE.json configs[1] at full size (64 channels x 60 s @ 48 kHz, 33 bands, float64; 48.7 GB of band
     signals): whole rows against the oracle, and the size-independent properties block-carry == one-shot and
