@@ -51,6 +51,15 @@ while time.time() < t_end:
         e2 = max(rel(y2.cpu().numpy()[:, b], yd[:, b]) for b in range(B))
         if not e2 <= 1e-6:
             print("FAIL fd K=%d B=%d C=%d n=%d err=%.2e" % (K, B, C, n, e2)); sys.exit(1)
+        # per-band arithmetic (PFB_ARITH_AUTO): whatever the calibration decides for this random bank, every band
+        # stays within the float32 bar of 1e-4 against the double result
+        y3, s3 = p.bank_filter(bank, torch.from_numpy(xf).cuda(), torch.from_numpy(st0.copy()).cuda(), arith64="auto")
+        y3 = y3.cpu().numpy()
+        e3 = max(rel(y3[:, b], yd[:, b]) for b in range(B))
+        auto_cases = globals().get("auto_cases", 0) + 1
+        auto_worst = max(globals().get("auto_worst", 0.0), e3)
+        if not (e3 <= 1e-4 and np.isfinite(y3).all() and s3.dtype == torch.float64):
+            print("FAIL auto K=%d B=%d C=%d n=%d err=%.2e f32 bands %d %s" % (K, B, C, n, e3, bank.f32_bands(), bank.last_launch())); sys.exit(1)
 # gammatone banks: random batch sizes, lengths and orders through the planner
 from pyfilterbank_b200 import gammatone as gt
 t_end = time.time() + float(os.environ.get("SECONDS_FOS", 30))
@@ -133,4 +142,5 @@ while time.time() < t_end:
         dec_cases += 1
 os.environ.pop("PFB_WEIGHT_FUSED", None)
 print("gammatone cases %d, band-level cases %d, weighted cases %d, decimated cases %d" % (fos_cases, lev_cases, fused_cases, dec_cases))
+print("per-band arithmetic cases %d, worst band error %.2e" % (globals().get("auto_cases", 0), globals().get("auto_worst", 0.0)))
 print("fuzz ok: %d cases, worst band error %.2e, launch kinds (mode, path) %s" % (cases, worst, modes))
