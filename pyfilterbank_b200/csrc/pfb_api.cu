@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -435,6 +436,7 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
     }
     Tables t;
     t.last_use = ++b->table_clock;
+    const auto t_build0 = std::chrono::steady_clock::now();
     // on a CUDA error the partial allocations held in t are released before returning
 #define PFB_CUDA_T(call)                                                                         \
     do {                                                                                         \
@@ -529,6 +531,11 @@ int ensure_tables(pfb_bank *b, int arith, long long L, int tt, const Tables **ou
     }
     PFB_CUDA_T(cudaStreamSynchronize(0));   // pageable uploads have landed before any stream's kernel reads the tables
 #undef PFB_CUDA_T
+    if (env_int("PFB_TABLE_TRACE", 0))   // which shapes build table sets, how large they are and how long the host takes
+        fprintf(stderr, "[pfb tables] built set (arith %d, chunk %lld, tile step %d): %.1f MB in %.1f ms; cache now %zu sets, %.1f MB\n",
+                arith, L, tt, t.bytes / 1048576.0,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count(),
+                b->tables.size() + 1, (cached_bytes + t.bytes) / 1048576.0);
     auto ins = b->tables.emplace(key, std::move(t));
     *out = &ins.first->second;
     return PFB_OK;
