@@ -17,13 +17,12 @@ print("f32 bands:", bank.f32_bands(), flush=True)
 VARIANTS = [("arith_f64", True, {}), ("arith_auto", "auto", {}), ("arith_f32", False, {})]
 for wide, nb in ((0, 7), (0, 9), (0, 11), (1, 11)) if os.environ.get("VARIANTS") else ():
     VARIANTS.append(("auto wide=%d nb=%d" % (wide, nb), "auto", {"PFB_TMA_WIDE": str(wide), "PFB_TMA_NB": str(nb)}))
-VARIANTS.append(("auto unpaired", "auto", {"PFB_TMA_PAIR": "0"}))
 for J in (32, 64, 96, 128, 160, 192) if os.environ.get("JSWEEP") else ():
     VARIANTS.append(("auto J=%d" % J, "auto", {"PFB_TMA_J": str(J)}))
 if os.environ.get("VARIANTS"):
     VARIANTS.append(("f64 wide=0 nb=7", True, {"PFB_TMA_WIDE": "0", "PFB_TMA_NB": "7"}))
 for name, a64, env in VARIANTS:
-    for k in ("PFB_TMA_WIDE", "PFB_TMA_NB", "PFB_TMA_J", "PFB_TMA_PAIR"):
+    for k in ("PFB_TMA_WIDE", "PFB_TMA_NB", "PFB_TMA_J"):
         os.environ.pop(k, None)
     os.environ.update(env)
     yp, _ = p.bank_filter(bank, xp, None, arith64=a64)
