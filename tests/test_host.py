@@ -197,3 +197,22 @@ def test_bench_reference_arm_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_flag_words_and_auto_arithmetic_abi():
+    """Python flag words match include/pfb_sos.h; arith64='auto' asks for float64 states AND the per-band choice;
+    pfb_bank_f32_bands validates its argument and needs a device (no host-side arithmetic in the product)."""
+    import re
+    import torch
+    from pyfilterbank_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pfb_sos.h")).read()
+    words = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define (PFB_[A-Z0-9_]+) (0x[0-9a-fA-F]+)", hdr)}
+    assert words["PFB_EXACT"] == _lib.EXACT and words["PFB_ARITH_F64"] == _lib.ARITH_F64
+    assert words["PFB_DECIMATE2"] == _lib.DECIMATE2 and words["PFB_ARITH_AUTO"] == _lib.ARITH_AUTO
+    assert _lib.flags_of("auto", False, "auto") == _lib.ARITH_F64 | _lib.ARITH_AUTO
+    assert _lib.flags_of("scan", False, True) == _lib.MODE_SCAN | _lib.ARITH_F64
+    L = _lib.lib()
+    assert L.pfb_bank_f32_bands(None) == -1
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        assert L.pfb_bank_create(ctypes.byref(h), np.array([1, 0, 0, 1, 0, 0.]).ctypes.data, 1, 1, 1, 0) == -3
