@@ -1936,7 +1936,14 @@ int pfb_decbank_filter(pfb_decbank *d, const double *x, int64_t ldx, void *const
         for (int m = 0; m <= d->M; ++m)
             if (d->nb[m] > 0 && m == 0 && (!y[m] || !band_states[m] || ldy[m] < n))
                 return fail(PFB_ERR_INVALID, "pfb_decbank_filter: stage %d needs an output of %lld samples per row", m, (long long)n);
-        return d->split_filter(x, ldx, y, ldy, band_states, aa_states, phases, n, C, flags, stream);
+        const int rcs = d->split_filter(x, ldx, y, ldy, band_states, aa_states, phases, n, C, flags, stream);
+        if (rcs != PFB_OK && d->s_aa) {
+            // a failed call must not leave work of its side streams running on buffers the caller may now release
+            cudaStreamSynchronize(d->s_aa);
+            for (cudaStream_t st : d->s_band)
+                if (st) cudaStreamSynchronize(st);
+        }
+        return rcs;
     }
     d->last_kernels = d->last_fused = 0;
     const double *in = x;
