@@ -67,9 +67,12 @@ static void fill_tma_table(const TmaParams &p, const double *coef_host, CoefTabl
         for (int k = 0; k < K; ++k) {
             const double *c = &coef_host[((size_t)r * p.Ktot + p.k0 + k) * 5];
             for (int i = 0; i < 5; ++i) tab.c[r * K + k][i] = (PFB_A)c[i];
-            if (SCALED) {   // numerator normalised by b0: (., b1/b0, b2/b0)
-                tab.c[r * K + k][1] = (PFB_A)(c[1] / c[0]);
-                tab.c[r * K + k][2] = (PFB_A)(c[2] / c[0]);
+            if (SCALED) {
+                // numerator normalised by b0 and written on the OLD states: with w0 = x - a1 w1 - a2 w2,
+                // y = w0 + (b1/b0) w1 + (b2/b0) w2 = x + (b1/b0 - a1) w1 + (b2/b0 - a2) w2 (scaled_step).  For the
+                // band passes' (1 +- z^-1)^2 numerators the two differences are exact in double (Sterbenz).
+                tab.c[r * K + k][1] = (PFB_A)((long double)c[1] / (long double)c[0] - (long double)c[3]);
+                tab.c[r * K + k][2] = (PFB_A)((long double)c[2] / (long double)c[0] - (long double)c[4]);
                 total_gain *= c[0];
             }
         }

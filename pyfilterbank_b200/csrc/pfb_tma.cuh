@@ -257,12 +257,17 @@ __device__ __forceinline__ void bulk_wait_read_upto(int pending) {
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// One section in gain-normalised form: c = {total gain (section 0 only), b1/b0, b2/b0, a1, a2}.
+// One section in gain-normalised form: c = {total gain (section 0 only), b1/b0 - a1, b2/b0 - a2, a1, a2}.
 template <typename A>
 __device__ __forceinline__ A scaled_step(A x, const A *c, A &w1, A &w2) {
+    // c = {., b1/b0 - a1, b2/b0 - a2, a1, a2}: the output is formed from the input and the OLD states, not from w0 --
+    // the same four FMAs, but x -> y is two dependent operations instead of four, which halves the latency of a
+    // wavefront step of the cascade (a band warp that has its SM sub-partition's FP64 pipe to itself or shares it with
+    // one other is bound by that chain, not by the pipe); and y no longer cancels w0 - 2 w1 + w2 at the states'
+    // magnitude (1e6 times the signal in the low bands) but at that of its own terms (~300 times).
     const A t = fma(-c[4], w2, x);
     const A w0 = fma(-c[3], w1, t);
-    const A y = fma(c[2], w2, fma(c[1], w1, w0));
+    const A y = fma(c[1], w1, fma(c[2], w2, x));
     w2 = w1;
     w1 = w0;
     return y;
